@@ -1,0 +1,598 @@
+// C ABI: context, clouds, nearest neighbour, rigid ICP (product code).
+#include "cb_internal.hpp"
+#include "icp_kernels.cuh"
+#include "stats_kernels.cuh"
+#include "host_solve.hpp"
+#include <cstring>
+#include <cfloat>
+#include <cmath>
+#include <algorithm>
+#include <vector>
+#include <string>
+
+namespace cb {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int ensure_scratch(cb_context* ctx, size_t partial_doubles) {
+  if (ctx->partials_cap >= partial_doubles) return CB_OK;
+  if (ctx->d_partials) CB_CUDA(cudaFree(ctx->d_partials));
+  size_t cap = std::max<size_t>(partial_doubles, 4096 * 32);
+  CB_CUDA(cudaMalloc(&ctx->d_partials, cap * sizeof(double)));
+  ctx->partials_cap = cap;
+  return CB_OK;
+}
+
+int fetch_result(cb_context* ctx, int count, bool allreduce, double* out) {
+  if (allreduce && ctx->world > 1) CB_TRY(nccl_allreduce_sum_f64(ctx, ctx->d_result, (size_t)count));
+  CB_CUDA(cudaMemcpyAsync(ctx->h_result, ctx->d_result, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_result, count * sizeof(double));
+  return CB_OK;
+}
+
+static Rigid to_rigid(const float* T12) {
+  Rigid r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
+    r.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
+  }
+  return r;
+}
+
+}  // namespace cb
+
+using namespace cb;
+
+struct cb_icp {
+  cb_context* ctx = nullptr;
+  const cb_cloud* dst = nullptr;
+  const cb_cloud* src = nullptr;
+  float dst_mean[3] = {0, 0, 0};
+  float src_mean[3] = {0, 0, 0};
+  int* d_nn_pos = nullptr;  // per sorted src point: sorted dst position of its match, -1 none
+  float* d_nn_d2 = nullptr;
+  bool nn_valid = false;
+  std::vector<cudaEvent_t> events;
+  std::vector<double> iter_ms;
+};
+
+extern "C" {
+
+const char* cb_last_error(void) { return cb::g_err.c_str(); }
+const char* cb_version(void) { return "cilantro_b200 0.1 (sm_100a)"; }
+
+// ---- context ------------------------------------------------------------------------------------
+int cb_context_create(int device, cb_context** out) {
+  CB_CHECK(out, CB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no CUDA device available (%s); cilantro_b200 has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return CB_ERR_NO_DEVICE;
+  }
+  CB_CHECK(device >= 0 && device < count, CB_ERR_INVALID, "device ordinal out of range");
+  CB_CUDA(cudaSetDevice(device));
+  cb_context* ctx = new cb_context;
+  ctx->device = device;
+  cudaDeviceProp prop;
+  CB_CUDA(cudaGetDeviceProperties(&prop, device));
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  ctx->hbm_bytes = prop.totalGlobalMem;
+  snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
+  CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CB_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
+  CB_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
+  CB_CUDA(cudaMalloc(&ctx->d_result, 64 * sizeof(double)));
+  CB_CUDA(cudaMemset(ctx->d_result, 0, 64 * sizeof(double)));
+  CB_CUDA(cudaMallocHost(&ctx->h_result, 64 * sizeof(double)));
+  CB_CUDA(cudaEventCreate(&ctx->ev0));
+  CB_CUDA(cudaEventCreate(&ctx->ev1));
+  CB_CUDA(cudaEventCreate(&ctx->ev2));
+  *out = ctx;
+  return CB_OK;
+}
+
+void cb_context_destroy(cb_context* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  nccl_destroy(ctx);
+  if (ctx->d_partials) cudaFree(ctx->d_partials);
+  if (ctx->d_counter) cudaFree(ctx->d_counter);
+  if (ctx->d_result) cudaFree(ctx->d_result);
+  if (ctx->h_result) cudaFreeHost(ctx->h_result);
+  if (ctx->d_flush) cudaFree(ctx->d_flush);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int cb_context_synchronize(cb_context* ctx) {
+  CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CB_OK;
+}
+
+int cb_context_device_info(cb_context* ctx, int* sm_count, size_t* hbm_bytes, char* name64) {
+  CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (hbm_bytes) *hbm_bytes = ctx->hbm_bytes;
+  if (name64) snprintf(name64, 64, "%s", ctx->name);
+  return CB_OK;
+}
+
+uint64_t cb_context_kernel_launches(cb_context* ctx) { return ctx ? ctx->launches : 0; }
+
+int cb_context_flush_l2(cb_context* ctx) {
+  CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->d_flush) {
+    ctx->flush_bytes = std::max<size_t>((size_t)256 << 20, 2 * ctx->l2_bytes);
+    CB_CUDA(cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+  }
+  CB_CUDA(cudaMemsetAsync(ctx->d_flush, 0x5a, ctx->flush_bytes, ctx->stream));
+  return CB_OK;
+}
+
+int cb_comm_unique_id(void* out_128_bytes) { return nccl_unique_id(out_128_bytes); }
+
+int cb_context_init_comm(cb_context* ctx, const void* id, int rank, int world) {
+  CB_CHECK(ctx && id, CB_ERR_INVALID, "null argument");
+  CB_CHECK(world >= 1 && rank >= 0 && rank < world, CB_ERR_INVALID, "bad rank/world");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  return nccl_init(ctx, id, rank, world);
+}
+
+int cb_context_comm_info(cb_context* ctx, int* rank, int* world) {
+  CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
+  if (rank) *rank = ctx->rank;
+  if (world) *world = ctx->world;
+  return CB_OK;
+}
+
+// ---- clouds -------------------------------------------------------------------------------------
+static int cloud_create_common(cb_context* ctx, const float* xyz, const float* normals, size_t n, uint64_t off,
+                               cudaMemcpyKind kind, cb_cloud** out) {
+  CB_CHECK(ctx && out, CB_ERR_INVALID, "null argument");
+  CB_CHECK(n == 0 || xyz, CB_ERR_INVALID, "xyz is null");
+  CB_CHECK(n < (1ull << 31), CB_ERR_INVALID, "point sets of >= 2^31 points are not supported");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  cb_cloud* c = new cb_cloud;
+  c->ctx = ctx;
+  c->n = n;
+  c->index_offset = off;
+  if (n > 0) {
+    CB_CUDA(cudaMalloc(&c->d_raw, 3 * n * sizeof(float)));
+    CB_CUDA(cudaMemcpyAsync(c->d_raw, xyz, 3 * n * sizeof(float), kind, ctx->stream));
+    if (normals) {
+      CB_CUDA(cudaMalloc(&c->d_raw_nrm, 3 * n * sizeof(float)));
+      CB_CUDA(cudaMemcpyAsync(c->d_raw_nrm, normals, 3 * n * sizeof(float), kind, ctx->stream));
+    }
+    // the caller's buffers may be released as soon as this returns
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *out = c;
+  return CB_OK;
+}
+
+int cb_cloud_create(cb_context* ctx, const float* xyz, const float* normals, size_t n, uint64_t index_offset,
+                    cb_cloud** out) {
+  return cloud_create_common(ctx, xyz, normals, n, index_offset, cudaMemcpyHostToDevice, out);
+}
+
+int cb_cloud_create_from_device(cb_context* ctx, const float* d_xyz, const float* d_normals, size_t n,
+                                uint64_t index_offset, cb_cloud** out) {
+  return cloud_create_common(ctx, d_xyz, d_normals, n, index_offset, cudaMemcpyDeviceToDevice, out);
+}
+
+void cb_cloud_destroy(cb_cloud* c) {
+  if (!c) return;
+  cudaSetDevice(c->ctx->device);
+  cudaStreamSynchronize(c->ctx->stream);
+  if (c->d_raw) cudaFree(c->d_raw);
+  if (c->d_raw_nrm) cudaFree(c->d_raw_nrm);
+  if (c->d_pts) cudaFree(c->d_pts);
+  if (c->d_nrm) cudaFree(c->d_nrm);
+  if (c->d_cell_start) cudaFree(c->d_cell_start);
+  delete c;
+}
+
+size_t cb_cloud_size(const cb_cloud* c) { return c ? c->n : 0; }
+
+int cb_cloud_grid_info(const cb_cloud* c, float* cell_edge, int* dims3, double* mean_occupancy) {
+  CB_CHECK(c, CB_ERR_INVALID, "cloud is null");
+  CB_TRY(ensure_index(const_cast<cb_cloud*>(c)));
+  if (cell_edge) *cell_edge = 1.0f / c->inv_h;
+  if (dims3) {
+    dims3[0] = c->nx;
+    dims3[1] = c->ny;
+    dims3[2] = c->nz;
+  }
+  if (mean_occupancy) *mean_occupancy = c->mean_occ;
+  return CB_OK;
+}
+
+// ---- nearest neighbour ----------------------------------------------------------------------------
+static int knn1_device(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, float max_d2,
+                       int** d_idx_out, float** d_d2_out) {
+  CB_CHECK(ctx && ref && qry, CB_ERR_INVALID, "null argument");
+  CB_CHECK(ref->ctx == ctx && qry->ctx == ctx, CB_ERR_INVALID, "cloud belongs to another context");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  CB_TRY(ensure_index(const_cast<cb_cloud*>(ref)));
+  CB_TRY(ensure_index(const_cast<cb_cloud*>(qry)));
+  int* d_idx = nullptr;
+  float* d_d2 = nullptr;
+  const size_t nq = std::max<size_t>(qry->n, 1);
+  CB_CUDA(cudaMallocAsync(&d_idx, nq * sizeof(int), ctx->stream));
+  CB_CUDA(cudaMallocAsync(&d_d2, nq * sizeof(float), ctx->stream));
+  IcpArgs a{};
+  a.dst = grid_view(ref);
+  a.src_pts = qry->d_pts;
+  a.src_nrm = nullptr;
+  a.n_src = (uint32_t)qry->n;
+  a.T = to_rigid(T12);
+  a.Tin = to_rigid(nullptr);
+  a.max_d2 = max_d2;
+  a.out_idx = d_idx;
+  a.out_d2 = d_d2;
+  CB_TRY(launch_icp_pass(ctx, a, kModeKnn, true, false, false));
+  *d_idx_out = d_idx;
+  *d_d2_out = d_d2;
+  return CB_OK;
+}
+
+int cb_knn1_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, float max_d2,
+                   int64_t* idx, float* d2) {
+  int* d_idx = nullptr;
+  float* d_d2 = nullptr;
+  CB_TRY(knn1_device(ctx, ref, qry, T12, max_d2, &d_idx, &d_d2));
+  const size_t nq = qry->n;
+  std::vector<int> h_idx(nq);
+  if (nq) {
+    CB_CUDA(cudaMemcpyAsync(h_idx.data(), d_idx, nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (d2) CB_CUDA(cudaMemcpyAsync(d2, d_d2, nq * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CB_CUDA(cudaFreeAsync(d_idx, ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_d2, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (idx)
+    for (size_t i = 0; i < nq; i++) idx[i] = h_idx[i] < 0 ? -1 : (int64_t)h_idx[i] + (int64_t)ref->index_offset;
+  return CB_OK;
+}
+
+int cb_find_correspondences(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12,
+                            float max_d2, uint64_t* index_first, uint64_t* index_second, float* value,
+                            size_t* count) {
+  CB_CHECK(count, CB_ERR_INVALID, "count is null");
+  *count = 0;
+  if (ref && ref->n == 0) return CB_OK;  // correspondence_search_kd_tree_utilities.hpp:16-19
+  int* d_idx = nullptr;
+  float* d_d2 = nullptr;
+  CB_TRY(knn1_device(ctx, ref, qry, T12, max_d2, &d_idx, &d_d2));
+  const size_t nq = qry->n;
+  std::vector<int> h_idx(nq);
+  std::vector<float> h_d2(nq);
+  if (nq) {
+    CB_CUDA(cudaMemcpyAsync(h_idx.data(), d_idx, nq * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(h_d2.data(), d_d2, nq * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CB_CUDA(cudaFreeAsync(d_idx, ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_d2, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  size_t k = 0;  // compaction in query order (:45-50)
+  for (size_t i = 0; i < nq; i++) {
+    if (h_idx[i] < 0) continue;
+    if (index_first) index_first[k] = (uint64_t)h_idx[i] + ref->index_offset;
+    if (index_second) index_second[k] = (uint64_t)i + qry->index_offset;
+    if (value) value[k] = h_d2[i];
+    ++k;
+  }
+  *count = k;
+  return CB_OK;
+}
+
+int cb_transform_points(cb_context* ctx, const float* T12, const float* xyz, size_t n, float* out) {
+  CB_CHECK(ctx && T12 && (n == 0 || (xyz && out)), CB_ERR_INVALID, "null argument");
+  if (n == 0) return CB_OK;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  float *d_in = nullptr, *d_out = nullptr;
+  CB_CUDA(cudaMallocAsync(&d_in, 3 * n * sizeof(float), ctx->stream));
+  CB_CUDA(cudaMallocAsync(&d_out, 3 * n * sizeof(float), ctx->stream));
+  CB_CUDA(cudaMemcpyAsync(d_in, xyz, 3 * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CB_TRY(launch_transform_points(ctx, to_rigid(T12), d_in, n, d_out));
+  CB_CUDA(cudaMemcpyAsync(out, d_out, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_in, ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_out, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CB_OK;
+}
+
+// ---- ICP ------------------------------------------------------------------------------------------
+void cb_icp_default_params(cb_icp_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->metric = CB_ICP_POINT_TO_POINT;
+  p->max_iter = 15;                  // icp_base.hpp:24
+  p->tol = 1e-5f;                    // icp_base.hpp:25
+  p->max_d2 = (float)(0.01 * 0.01);  // correspondence_search_kd_tree.hpp:49
+  p->w_pt = 0.f;                     // icp_single_transform_combined_metric.hpp:46
+  p->w_pl = 1.f;                     // :47
+  p->max_opt_iter = 1;               // :44
+  p->opt_tol = 1e-5f;                // :45
+  t34_identity(p->T_init);
+}
+
+// mean of a cloud over all ranks (rowwise().mean(), icp_single_transform_combined_metric.hpp:51-58)
+static int global_mean(cb_context* ctx, const cb_cloud* c, bool allreduce, float* mean3) {
+  const float zero[3] = {0, 0, 0};
+  CB_TRY(launch_moments(ctx, c->d_raw, c->n, zero));
+  double m[kMomentValues];
+  CB_TRY(fetch_result(ctx, kMomentValues, allreduce, m));
+  for (int r = 0; r < 3; r++) mean3[r] = (m[0] > 0) ? (float)(m[1 + r] / m[0]) : 0.f;
+  return CB_OK;
+}
+
+int cb_icp_create(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, cb_icp** out) {
+  CB_CHECK(ctx && dst && src && out, CB_ERR_INVALID, "null argument");
+  CB_CHECK(dst->ctx == ctx && src->ctx == ctx, CB_ERR_INVALID, "cloud belongs to another context");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  CB_TRY(ensure_index(const_cast<cb_cloud*>(dst)));
+  CB_TRY(ensure_index(const_cast<cb_cloud*>(src)));
+  cb_icp* icp = new cb_icp;
+  icp->ctx = ctx;
+  icp->dst = dst;
+  icp->src = src;
+  // dst is replicated on every rank, src is sharded: only the src mean needs the all-reduce
+  CB_TRY(global_mean(ctx, dst, false, icp->dst_mean));
+  CB_TRY(global_mean(ctx, src, true, icp->src_mean));
+  CB_CUDA(cudaMalloc(&icp->d_nn_pos, std::max<size_t>(src->n, 1) * sizeof(int)));
+  CB_CUDA(cudaMalloc(&icp->d_nn_d2, std::max<size_t>(src->n, 1) * sizeof(float)));
+  *out = icp;
+  return CB_OK;
+}
+
+void cb_icp_destroy(cb_icp* icp) {
+  if (!icp) return;
+  cudaSetDevice(icp->ctx->device);
+  cudaStreamSynchronize(icp->ctx->stream);
+  if (icp->d_nn_pos) cudaFree(icp->d_nn_pos);
+  if (icp->d_nn_d2) cudaFree(icp->d_nn_d2);
+  for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
+  delete icp;
+}
+
+static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, const float* Tin, IcpArgs* a) {
+  std::memset(a, 0, sizeof(*a));
+  a->dst = grid_view(icp->dst);
+  a->src_pts = icp->src->d_pts;
+  a->src_nrm = (prm->metric == CB_ICP_COMBINED) ? icp->src->d_nrm : nullptr;
+  a->n_src = (uint32_t)icp->src->n;
+  a->T = to_rigid(T);
+  a->Tin = to_rigid(Tin);
+  a->max_d2 = prm->max_d2;
+  a->w_pt = prm->w_pt;
+  a->w_pl = prm->w_pl;
+  for (int r = 0; r < 3; r++) a->dm[r] = icp->dst_mean[r];
+  float smt[3];
+  apply_point(T, icp->src_mean, smt);  // this->transform_ * src_mean_  (:189/:196)
+  for (int r = 0; r < 3; r++) a->sm[r] = smt[r];
+  a->nn_pos = icp->d_nn_pos;
+  a->nn_d2 = icp->d_nn_d2;
+  return CB_OK;
+}
+
+// One estimator call of updateEstimate(): returns tform_iter (already un-centred), and the
+// correspondence count of the search pass.
+static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, float* Titer, double* n_corr) {
+  cb_context* ctx = icp->ctx;
+  IcpArgs a;
+  double sums[kMaxValues];
+  if (prm->metric == CB_ICP_POINT_TO_POINT) {
+    CB_TRY(icp_fill_args(icp, prm, T, nullptr, &a));
+    CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
+    CB_TRY(fetch_result(ctx, kP2PValues, true, sums));
+    kabsch_from_moments(sums, Titer);
+    *n_corr = sums[0];
+    icp->nn_valid = true;
+    return CB_OK;
+  }
+  // combined / symmetric Gauss-Newton (transform_estimation.hpp:238-367 / :608-739)
+  const bool w_pt_on = prm->w_pt > 0.f, w_pl_on = prm->w_pl > 0.f;
+  float Tin[12];
+  t34_identity(Tin);
+  t34_identity(Titer);
+  const bool dst_has_normals = icp->dst->d_nrm != nullptr;
+  // has_point_to_plane_terms && dst_p.cols() != dst_n.cols() -> return false with identity (:269-272)
+  const bool bail_no_normals = w_pl_on && !dst_has_normals;
+  const int max_opt = std::max(prm->max_opt_iter, 0);
+  bool any_pass = false;
+  for (int it = 0; it < std::max(max_opt, 1); ++it) {
+    CB_TRY(icp_fill_args(icp, prm, T, Tin, &a));
+    const bool search = (it == 0);
+    // the first pass always runs (it is also the correspondence search of this ICP iteration)
+    CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
+    CB_TRY(fetch_result(ctx, kCombinedValues, true, sums));
+    if (search) {
+      *n_corr = sums[0];
+      icp->nn_valid = true;
+    }
+    any_pass = true;
+    const bool has_terms = sums[0] > 0.0 && (w_pt_on || w_pl_on);
+    if (!has_terms || bail_no_normals) {
+      t34_identity(Titer);
+      return CB_OK;
+    }
+    if (max_opt == 0) break;  // max_iter == 0: loop body never runs, only the un-centring (:365)
+    float dn = 0.f;
+    float Tnext[12];
+    gauss_newton_update(sums, Tin, Tnext, &dn);
+    std::memcpy(Tin, Tnext, sizeof(Tin));
+    if (dn < prm->opt_tol) break;  // :360-363
+  }
+  (void)any_pass;
+  std::memcpy(Titer, Tin, sizeof(Tin));
+  float smt[3];
+  apply_point(T, icp->src_mean, smt);
+  uncenter(Titer, icp->dst_mean, smt);
+  return CB_OK;
+}
+
+int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
+  CB_CHECK(icp && prm && res, CB_ERR_INVALID, "null argument");
+  CB_CHECK(prm->metric == CB_ICP_POINT_TO_POINT || prm->metric == CB_ICP_COMBINED, CB_ERR_INVALID, "bad metric");
+  cb_context* ctx = icp->ctx;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  const uint64_t launches0 = ctx->launches;
+  const int max_iter = std::max(prm->max_iter, 0);
+  while ((int)icp->events.size() < 2 * max_iter) {
+    cudaEvent_t e;
+    CB_CUDA(cudaEventCreate(&e));
+    icp->events.push_back(e);
+  }
+  float T[12];
+  std::memcpy(T, prm->T_init, sizeof(T));  // icp_base.hpp:71
+  int iters = 0;
+  float last_delta = INFINITY;
+  double n_corr = 0;
+  icp->nn_valid = false;
+  while (iters < max_iter) {  // icp_base.hpp:76-84
+    if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
+    CB_CUDA(cudaEventRecord(icp->events[2 * iters], ctx->stream));
+    float Titer[12];
+    // updateCorrespondences() + updateEstimate(): one fused pass (+ stored-correspondence passes
+    // for inner Gauss-Newton iterations), reduction, host solve
+    CB_TRY(icp_update(icp, prm, T, Titer, &n_corr));
+    CB_CUDA(cudaEventRecord(icp->events[2 * iters + 1], ctx->stream));
+    reorthonormalize(Titer);           // :207-211
+    compose(Titer, T, T);              // :213
+    last_delta = update_norm(Titer);   // :214-216
+    iters++;
+    if (last_delta < prm->tol) break;  // icp_base.hpp:83
+  }
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  icp->iter_ms.assign(iters, 0.0);
+  double total = 0;
+  for (int i = 0; i < iters; i++) {
+    float ms = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&ms, icp->events[2 * i], icp->events[2 * i + 1]));
+    icp->iter_ms[i] = ms;
+    total += ms;
+  }
+  std::memcpy(res->T, T, sizeof(T));
+  res->iterations = iters;
+  res->last_delta = last_delta;
+  res->converged = last_delta < prm->tol;
+  res->num_corr = (uint64_t)(n_corr + 0.5);
+  res->gpu_ms_total = total;
+  res->gpu_ms_search = total;
+  res->kernel_launches = ctx->launches - launches0;
+  return CB_OK;
+}
+
+int cb_icp_iteration_times(cb_icp* icp, double* ms, int cap) {
+  CB_CHECK(icp && ms, CB_ERR_INVALID, "null argument");
+  const int n = std::min<int>(cap, (int)icp->iter_ms.size());
+  for (int i = 0; i < n; i++) ms[i] = icp->iter_ms[i];
+  return n;
+}
+
+int cb_icp_accumulate(cb_icp* icp, const cb_icp_params* prm, const float* T12, double* sums, int cap) {
+  CB_CHECK(icp && prm && T12 && sums, CB_ERR_INVALID, "null argument");
+  cb_context* ctx = icp->ctx;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  IcpArgs a;
+  CB_TRY(icp_fill_args(icp, prm, T12, nullptr, &a));
+  double tmp[kMaxValues];
+  int nv;
+  if (prm->metric == CB_ICP_POINT_TO_POINT) {
+    nv = kP2PValues;
+    CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
+  } else {
+    nv = kCombinedValues;
+    CB_CHECK(!(prm->w_pl > 0.f) || icp->dst->d_nrm, CB_ERR_INVALID, "dst has no normals");
+    CB_TRY(launch_icp_pass(ctx, a, kModeCombined, true, prm->w_pt > 0.f, prm->w_pl > 0.f));
+  }
+  CB_CHECK(cap >= nv, CB_ERR_INVALID, "sums buffer too small");
+  CB_TRY(fetch_result(ctx, nv, true, tmp));
+  std::memcpy(sums, tmp, nv * sizeof(double));
+  icp->nn_valid = true;
+  return nv;
+}
+
+int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_second, float* value, size_t* count) {
+  CB_CHECK(icp && count, CB_ERR_INVALID, "null argument");
+  CB_CHECK(icp->nn_valid, CB_ERR_INVALID, "no correspondences yet: call cb_icp_estimate first");
+  cb_context* ctx = icp->ctx;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  const size_t ns = icp->src->n;
+  *count = 0;
+  if (ns == 0) return CB_OK;
+  // nn_pos is indexed by sorted src position and holds sorted dst positions: translate on the host
+  std::vector<int> pos(ns);
+  std::vector<float> nd2(ns);
+  std::vector<float4> sp(ns);
+  CB_CUDA(cudaMemcpyAsync(pos.data(), icp->d_nn_pos, ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaMemcpyAsync(nd2.data(), icp->d_nn_d2, ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaMemcpyAsync(sp.data(), icp->src->d_pts, ns * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t nd = icp->dst->n;
+  std::vector<float4> dp(nd);
+  if (nd) CB_CUDA(cudaMemcpyAsync(dp.data(), icp->dst->d_pts, nd * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  // this path is a getter, not the hot loop: rebuild (dst idx, d2) per ORIGINAL src index
+  std::vector<int64_t> first(ns, -1);
+  std::vector<float> val(ns, 0.f);
+  for (size_t i = 0; i < ns; i++) {
+    if (pos[i] < 0) continue;
+    int oi, di;
+    std::memcpy(&oi, &sp[i].w, 4);
+    std::memcpy(&di, &dp[pos[i]].w, 4);
+    first[oi] = di;
+    val[oi] = nd2[i];
+  }
+  size_t k = 0;
+  for (size_t i = 0; i < ns; i++) {
+    if (first[i] < 0) continue;
+    if (index_first) index_first[k] = (uint64_t)first[i] + icp->dst->index_offset;
+    if (index_second) index_second[k] = (uint64_t)i + icp->src->index_offset;
+    if (value) value[k] = val[i];
+    ++k;
+  }
+  *count = k;
+  return CB_OK;
+}
+
+int cb_icp_residuals(cb_icp* icp, const cb_icp_params* prm, const float* T12, float* out) {
+  CB_CHECK(icp && prm && T12 && out, CB_ERR_INVALID, "null argument");
+  cb_context* ctx = icp->ctx;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  const size_t ns = icp->src->n;
+  if (ns == 0) return CB_OK;
+  CB_CHECK(prm->metric == CB_ICP_POINT_TO_POINT || icp->dst->d_nrm || icp->dst->n == 0, CB_ERR_INVALID,
+           "dst has no normals");
+  float* d_out = nullptr;
+  CB_CUDA(cudaMallocAsync(&d_out, ns * sizeof(float), ctx->stream));
+  CB_TRY(launch_residuals(ctx, grid_view(icp->dst), icp->src->d_pts,
+                          prm->metric == CB_ICP_COMBINED ? icp->src->d_nrm : nullptr, (uint32_t)ns, to_rigid(T12),
+                          prm->metric, prm->w_pt, prm->w_pl, d_out));
+  CB_CUDA(cudaMemcpyAsync(out, d_out, ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_out, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CB_OK;
+}
+
+}  // extern "C"

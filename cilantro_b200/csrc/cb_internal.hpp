@@ -1,0 +1,105 @@
+// Internal declarations shared by the translation units of libcilantro_b200.so.
+// Product code: never includes or links anything from oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstdarg>
+#include <vector>
+#include "../../include/cilantro_b200.h"
+
+namespace cb {
+
+void set_error(const char* fmt, ...);
+
+#define CB_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess) {                                                                  \
+      cb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));     \
+      return CB_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+#define CB_CHECK(cond, status, msg)                                        \
+  do {                                                                     \
+    if (!(cond)) {                                                         \
+      cb::set_error("%s:%d: %s", __FILE__, __LINE__, msg);                 \
+      return status;                                                       \
+    }                                                                      \
+  } while (0)
+
+#define CB_TRY(expr)            \
+  do {                          \
+    int s__ = (expr);           \
+    if (s__ != CB_OK) return s__; \
+  } while (0)
+
+// Uniform grid over a cloud. Points are stored cell-sorted as float4 (x, y, z, original index bits);
+// cells are x-major: id = (z * ny + y) * nx + x, so the three x-neighbours of a row are one
+// contiguous range of the sorted array.
+struct GridView {
+  const float4* pts;           // n, cell-sorted; .w = __int_as_float(original index)
+  const float4* nrm;           // n, same order (or nullptr)
+  const uint32_t* cell_start;  // ncells + 1
+  float ox, oy, oz;            // grid origin (bbox min)
+  float inv_h;                 // 1 / cell edge
+  float h_safe;                // cell edge * (1 - 2^-10): conservative edge for lower bounds
+  int nx, ny, nz;
+  uint32_t n;
+};
+
+}  // namespace cb
+
+struct cb_context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  size_t l2_bytes = 0;
+  size_t hbm_bytes = 0;
+  char name[64] = {0};
+  uint64_t launches = 0;
+  // reduction scratch: per-block partials -> last block -> result
+  double* d_partials = nullptr;
+  size_t partials_cap = 0;  // in doubles
+  unsigned int* d_counter = nullptr;
+  double* d_result = nullptr;  // 64 doubles
+  double* h_result = nullptr;  // pinned, 64 doubles
+  void* d_flush = nullptr;
+  size_t flush_bytes = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  // NCCL (loaded lazily with dlopen; see nccl_dyn.cpp)
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+struct cb_cloud {
+  cb_context* ctx = nullptr;
+  size_t n = 0;
+  uint64_t index_offset = 0;
+  float* d_raw = nullptr;      // 3n packed xyz, original order
+  float* d_raw_nrm = nullptr;  // 3n packed normals or nullptr
+  // grid index (built lazily by cb::ensure_index)
+  bool indexed = false;
+  float4* d_pts = nullptr;
+  float4* d_nrm = nullptr;
+  uint32_t* d_cell_start = nullptr;
+  float ox = 0, oy = 0, oz = 0, h = 1, inv_h = 1;
+  int nx = 1, ny = 1, nz = 1;
+  double mean_occ = 0;
+};
+
+namespace cb {
+
+int ensure_index(cb_cloud* c);
+GridView grid_view(const cb_cloud* c);
+int ensure_scratch(cb_context* ctx, size_t partial_doubles);
+
+// nccl_dyn.cpp
+int nccl_unique_id(void* out128);
+int nccl_init(cb_context* ctx, const void* id128, int rank, int world);
+int nccl_allreduce_sum_f64(cb_context* ctx, double* d_buf, size_t count);
+void nccl_destroy(cb_context* ctx);
+
+}  // namespace cb

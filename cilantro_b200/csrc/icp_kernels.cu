@@ -1,0 +1,242 @@
+// Fused ICP iteration kernels (product code, sm_100a).
+//
+// One launch per ICP iteration does, for every source point s_i:
+//   q_i = T s_i                               transformFeatures + transformPoints
+//                                             (common_transformable_feature_adaptors.hpp:28-34,
+//                                              core/space_transformations.hpp:203-216)
+//   (j, d2) = radius-bounded 1-NN of q_i      findNNCorrespondencesUnidirectional
+//                                             (correspondence_search_kd_tree_utilities.hpp:26-33)
+//   keep iff found and d2 < max_d2            (:29)
+//   accumulate the estimator's moments        Kabsch: transform_estimation.hpp:25-34
+//                                             Gauss-Newton: :298-343 (combined), :669-715 (symmetric)
+// and reduces them warp -> block -> grid (last-block pattern) in double precision. The serial
+// stream compaction of the reference (:45-50) disappears: the accumulation is order-free and the
+// correspondence list is only materialised when a caller asks for it.
+#include "icp_kernels.cuh"
+#include "reduce.cuh"
+#include <algorithm>
+
+namespace cb {
+
+namespace {
+
+constexpr int kBlock = kReduceBlock;
+
+__device__ __forceinline__ constexpr int ut(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
+
+template <int MODE, bool SEARCH>
+__global__ void __launch_bounds__(kBlock) icp_pass_kernel(const IcpArgs a, const bool has_pt, const bool has_pl) {
+  constexpr int NV = (MODE == kModeP2P) ? kP2PValues : (MODE == kModeCombined ? kCombinedValues : 1);
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; i++) acc[i] = 0.0;
+
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += stride) {
+    const float4 s = __ldg(a.src_pts + i);
+    float qx, qy, qz;
+    apply_rigid(a.T, s.x, s.y, s.z, qx, qy, qz);
+
+    int pos;
+    if (SEARCH) {
+      const Best best = grid_nearest(a.dst, qx, qy, qz, a.max_d2);
+      pos = (best.idx >= 0 && best.d2 < a.max_d2) ? best.pos : -1;
+      if (a.nn_pos) a.nn_pos[i] = pos;
+      if (a.nn_d2) a.nn_d2[i] = best.d2;
+      if (MODE == kModeKnn) {
+        const int oi = __float_as_int(s.w);
+        if (a.out_idx) a.out_idx[oi] = (pos >= 0) ? best.idx : -1;
+        if (a.out_d2) a.out_d2[oi] = (pos >= 0) ? best.d2 : a.max_d2;
+      }
+    } else {
+      pos = a.nn_pos[i];
+    }
+    if (MODE == kModeKnn || pos < 0) continue;
+
+    const float4 dp = __ldg(a.dst.pts + pos);
+    if constexpr (MODE == kModeP2P) {
+      const double dx = dp.x, dy = dp.y, dz = dp.z, x = qx, y = qy, z = qz;
+      acc[0] += 1.0;
+      acc[1] += dx; acc[2] += dy; acc[3] += dz;
+      acc[4] += x;  acc[5] += y;  acc[6] += z;
+      acc[7] += dx * x;  acc[8] += dx * y;  acc[9] += dx * z;
+      acc[10] += dy * x; acc[11] += dy * y; acc[12] += dy * z;
+      acc[13] += dz * x; acc[14] += dz * y; acc[15] += dz * z;
+    } else if constexpr (MODE == kModeCombined) {
+      // d = dst - dst_mean ; s = Tin * (q - T*src_mean)           transform_estimation.hpp:300,304
+      const float d0 = __fsub_rn(dp.x, a.dm[0]), d1 = __fsub_rn(dp.y, a.dm[1]), d2 = __fsub_rn(dp.z, a.dm[2]);
+      float s0, s1, s2;
+      apply_rigid(a.Tin, __fsub_rn(qx, a.sm[0]), __fsub_rn(qy, a.sm[1]), __fsub_rn(qz, a.sm[2]), s0, s1, s2);
+      const float v0 = __fadd_rn(d0, s0), v1 = __fadd_rn(d1, s1), v2 = __fadd_rn(d2, s2);
+      const float e0 = __fsub_rn(d0, s0), e1 = __fsub_rn(d1, s1), e2 = __fsub_rn(d2, s2);
+      acc[0] += 1.0;
+      double* A = acc + 1;
+      double* b = acc + 22;
+      if (has_pt) {
+        // eq_vecs E = [ [v]x ; I ] (6x3, :306-316)  ->  E E^T = [ |v|^2 I - v v^T , [v]x ; -[v]x , I ],
+        // E e = [ v x e ; e ]
+        const double w = a.w_pt;
+        const double V0 = v0, V1 = v1, V2 = v2, E0 = e0, E1 = e1, E2 = e2;
+        A[ut(0, 0)] += w * (V1 * V1 + V2 * V2);
+        A[ut(0, 1)] -= w * (V0 * V1);
+        A[ut(0, 2)] -= w * (V0 * V2);
+        A[ut(1, 1)] += w * (V0 * V0 + V2 * V2);
+        A[ut(1, 2)] -= w * (V1 * V2);
+        A[ut(2, 2)] += w * (V0 * V0 + V1 * V1);
+        A[ut(0, 4)] -= w * V2;
+        A[ut(0, 5)] += w * V1;
+        A[ut(1, 3)] += w * V2;
+        A[ut(1, 5)] -= w * V0;
+        A[ut(2, 3)] -= w * V1;
+        A[ut(2, 4)] += w * V0;
+        A[ut(3, 3)] += w;
+        A[ut(4, 4)] += w;
+        A[ut(5, 5)] += w;
+        b[0] += w * (V1 * E2 - V2 * E1);
+        b[1] += w * (V2 * E0 - V0 * E2);
+        b[2] += w * (V0 * E1 - V1 * E0);
+        b[3] += w * E0;
+        b[4] += w * E1;
+        b[5] += w * E2;
+      }
+      if (has_pl) {
+        const float4 np = __ldg(a.dst.nrm + pos);
+        float n0 = np.x, n1 = np.y, n2 = np.z;
+        if (a.src_nrm) {  // symmetric metric: n = n_dst + R_in (R_T n_src)        :705-706
+          const float4 sn = __ldg(a.src_nrm + i);
+          float r0, r1, r2, t0, t1, t2;
+          rotate_rigid(a.T, sn.x, sn.y, sn.z, r0, r1, r2);
+          rotate_rigid(a.Tin, r0, r1, r2, t0, t1, t2);
+          n0 = __fadd_rn(n0, t0);
+          n1 = __fadd_rn(n1, t1);
+          n2 = __fadd_rn(n2, t2);
+        }
+        // a = [ (d + s) x n ; n ],  r = n . (d - s)                                  :337-341
+        const float c0 = __fsub_rn(__fmul_rn(v1, n2), __fmul_rn(v2, n1));
+        const float c1 = __fsub_rn(__fmul_rn(v2, n0), __fmul_rn(v0, n2));
+        const float c2 = __fsub_rn(__fmul_rn(v0, n1), __fmul_rn(v1, n0));
+        const double av[6] = {c0, c1, c2, n0, n1, n2};
+        const double rd = (double)n0 * e0 + ((double)n1 * e1 + (double)n2 * e2);
+        const double w = a.w_pl;
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+          const double wr = w * av[r];
+#pragma unroll
+          for (int c = r; c < 6; c++) A[ut(r, c)] += wr * av[c];
+          b[r] += wr * rd;
+        }
+      }
+    }
+  }
+  if (MODE != kModeKnn) grid_reduce<NV>(acc, a.partials, a.counter, a.result);
+}
+
+__global__ void __launch_bounds__(kBlock) residual_kernel(const GridView dst, const float4* __restrict__ src_pts,
+                                                          const float4* __restrict__ src_nrm, uint32_t n_src,
+                                                          const Rigid T, int metric, float w_pt, float w_pl,
+                                                          float* __restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += stride) {
+    const float4 s = __ldg(src_pts + i);
+    const int oi = __float_as_int(s.w);
+    float qx, qy, qz;
+    apply_rigid(T, s.x, s.y, s.z, qx, qy, qz);
+    const Best best = grid_nearest(dst, qx, qy, qz, 3.402823466e+38f);
+    float res = __int_as_float(0x7fc00000);  // NaN when dst is empty (icp_*_metric.hpp:221-224)
+    if (best.idx >= 0) {
+      const float4 dp = __ldg(dst.pts + best.pos);
+      const float e0 = __fsub_rn(dp.x, qx), e1 = __fsub_rn(dp.y, qy), e2 = __fsub_rn(dp.z, qz);
+      const float sq = sum3(__fmul_rn(e0, e0), __fmul_rn(e1, e1), __fmul_rn(e2, e2));
+      if (metric == CB_ICP_POINT_TO_POINT) {
+        res = sq;
+      } else {
+        const float4 np = __ldg(dst.nrm + best.pos);
+        float n0 = np.x, n1 = np.y, n2 = np.z;
+        if (src_nrm) {  // the reference adds the UN-rotated source normal here (:236)
+          const float4 sn = __ldg(src_nrm + i);
+          n0 = __fadd_rn(n0, sn.x);
+          n1 = __fadd_rn(n1, sn.y);
+          n2 = __fadd_rn(n2, sn.z);
+        }
+        const float pd = sum3(__fmul_rn(n0, e0), __fmul_rn(n1, e1), __fmul_rn(n2, e2));
+        res = __fadd_rn(__fmul_rn(w_pt, sq), __fmul_rn(__fmul_rn(w_pl, pd), pd));
+      }
+    }
+    out[oi] = res;
+  }
+}
+
+__global__ void transform_points_kernel(const Rigid T, const float* __restrict__ in, size_t n, float* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float qx, qy, qz;
+    apply_rigid(T, in[3 * i], in[3 * i + 1], in[3 * i + 2], qx, qy, qz);
+    out[3 * i] = qx;
+    out[3 * i + 1] = qy;
+    out[3 * i + 2] = qz;
+  }
+}
+
+}  // namespace
+
+int icp_grid_blocks(const cb_context* ctx) {
+  // persistent-style launch: a whole number of waves of resident CTAs
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, icp_pass_kernel<kModeCombined, true>, kBlock, 0) !=
+            cudaSuccess ||
+        v < 1)
+      v = 2;
+    per_sm = v;
+  }
+  return ctx->sm_count * per_sm;
+}
+
+int launch_icp_pass(cb_context* ctx, const IcpArgs& a, int mode, bool search, bool has_pt, bool has_pl) {
+  if (a.n_src == 0 && mode == kModeKnn) return CB_OK;
+  int blocks = icp_grid_blocks(ctx);
+  const int need = (int)((a.n_src + kBlock - 1) / kBlock);
+  blocks = std::max(1, std::min(blocks, need));
+  CB_TRY(ensure_scratch(ctx, (size_t)blocks * kMaxValues));
+  IcpArgs args = a;
+  args.partials = ctx->d_partials;
+  args.counter = ctx->d_counter;
+  args.result = ctx->d_result;
+  if (mode == kModeKnn) {
+    icp_pass_kernel<kModeKnn, true><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
+  } else if (mode == kModeP2P) {
+    if (search)
+      icp_pass_kernel<kModeP2P, true><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
+    else
+      icp_pass_kernel<kModeP2P, false><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
+  } else {
+    if (search)
+      icp_pass_kernel<kModeCombined, true><<<blocks, kBlock, 0, ctx->stream>>>(args, has_pt, has_pl);
+    else
+      icp_pass_kernel<kModeCombined, false><<<blocks, kBlock, 0, ctx->stream>>>(args, has_pt, has_pl);
+  }
+  ctx->launches += 1;
+  CB_CUDA(cudaGetLastError());
+  return CB_OK;
+}
+
+int launch_residuals(cb_context* ctx, const GridView& dst, const float4* src_pts, const float4* src_nrm,
+                     uint32_t n_src, const Rigid& T, int metric, float w_pt, float w_pl, float* d_out) {
+  if (n_src == 0) return CB_OK;
+  int blocks = std::max(1, std::min(icp_grid_blocks(ctx), (int)((n_src + kBlock - 1) / kBlock)));
+  residual_kernel<<<blocks, kBlock, 0, ctx->stream>>>(dst, src_pts, src_nrm, n_src, T, metric, w_pt, w_pl, d_out);
+  ctx->launches += 1;
+  CB_CUDA(cudaGetLastError());
+  return CB_OK;
+}
+
+int launch_transform_points(cb_context* ctx, const Rigid& T, const float* d_in, size_t n, float* d_out) {
+  if (n == 0) return CB_OK;
+  int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 8, (n + 255) / 256));
+  transform_points_kernel<<<blocks, 256, 0, ctx->stream>>>(T, d_in, n, d_out);
+  ctx->launches += 1;
+  CB_CUDA(cudaGetLastError());
+  return CB_OK;
+}
+
+}  // namespace cb

@@ -1,0 +1,90 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), source points sharded in contiguous blocks,
+destination cloud replicated, ONE small all-reduce per iteration inside the library (NCCL, its own
+communicator). torch.distributed is used only for the rendezvous: broadcasting the 128-byte NCCL
+unique id and barriers / max-over-ranks timing in bench.py.
+"""
+import os
+
+import numpy as np
+
+
+def shard_bounds(n, rank, world):
+    """Contiguous block of rank `rank` when n items are split over `world` ranks (sizes differ by <= 1)."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    hi = lo + base + (1 if rank < rem else 0)
+    return lo, hi
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def init_process_group(backend=None):
+    """Join the torchrun rendezvous (MASTER_ADDR/PORT from the environment; 127.0.0.1 by contract)."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def broadcast_bytes(payload, src=0):
+    """Broadcast a bytes object from rank `src` over the default process group (any backend)."""
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return payload
+    box = [payload if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
+def attach_comm(ctx):
+    """Create the library's NCCL communicator on `ctx` across the torch.distributed world."""
+    import torch.distributed as dist
+
+    from . import capi
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return 0, 1
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = capi.comm_unique_id() if rank == 0 else None
+    uid = broadcast_bytes(uid, 0)
+    ctx.init_comm(uid, rank, world)
+    return rank, world
+
+
+def allreduce_sum_f64(values):
+    """Sum a small float64 vector over the default process group (host-side logic / CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.from_numpy(np.ascontiguousarray(values, np.float64).copy())
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        t = t.cpu()
+    return t.numpy()
+
+
+def max_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(x)
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

@@ -1,0 +1,74 @@
+"""Seeded synthetic workloads; shared by tests/ and bench.py. numpy only."""
+import numpy as np
+
+
+def rigid_from_axis_angle(axis, angle, t):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    R = np.eye(3) + np.sin(angle) * K + (1 - np.cos(angle)) * (K @ K)
+    T = np.zeros((3, 4), np.float64)
+    T[:, :3] = R
+    T[:, 3] = np.asarray(t, np.float64)
+    return T
+
+
+def invert(T):
+    T = np.asarray(T, np.float64)
+    R, t = T[:, :3], T[:, 3]
+    out = np.zeros((3, 4), np.float64)
+    out[:, :3] = R.T
+    out[:, 3] = -R.T @ t
+    return out
+
+
+def apply(T, pts):
+    T = np.asarray(T, np.float64)
+    return (np.asarray(pts, np.float64) @ T[:, :3].T + T[:, 3]).astype(np.float32)
+
+
+def t_ref_default():
+    """AngleAxis(0.02 rad about (1,1,1)/sqrt(3)), t = (0.01, -0.005, 0.008)."""
+    return rigid_from_axis_angle([1, 1, 1], 0.02, [0.01, -0.005, 0.008])
+
+
+def icp_pair(n, seed=1, noise=0.001, with_normals=False, n_src=None):
+    """dst uniform in [0,1)^3; src = T_ref^-1 dst + uniform noise in +-noise.
+
+    Returns dst (n,3), src (n_src,3), dst_normals or None, T_ref (3,4 float64): the transform ICP
+    should recover (src -> dst)."""
+    rng = np.random.default_rng(seed)
+    dst = rng.random((n, 3), dtype=np.float32)
+    T_ref = t_ref_default()
+    m = n if n_src is None else n_src
+    base = dst[:m] if m <= n else rng.random((m, 3), dtype=np.float32)
+    src = apply(invert(T_ref), base)
+    src = (src + (rng.random((m, 3), dtype=np.float32) - 0.5) * np.float32(2 * noise)).astype(np.float32)
+    nrm = None
+    if with_normals:
+        g = rng.standard_normal((n, 3)).astype(np.float32)
+        nrm = (g / np.linalg.norm(g, axis=1, keepdims=True)).astype(np.float32)
+    return dst, src, nrm, T_ref
+
+
+def kmeans_data(n, k, seed=1):
+    """uniform [0,1)^3 points; initial centroids = first k points of a seeded shuffle (config 4)."""
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3), dtype=np.float32)
+    idx = rng.permutation(n)[:k]
+    return pts, pts[idx].copy()
+
+
+def ransac_pairs(n, inlier_frac=0.3, seed=1, sigma=0.002):
+    """src uniform [0,1)^3; dst = T_ref src + N(0, sigma^2) for inliers, uniform otherwise (config 5)."""
+    rng = np.random.default_rng(seed)
+    src = rng.random((n, 3), dtype=np.float32)
+    T_ref = t_ref_default()
+    dst = apply(T_ref, src) + (rng.standard_normal((n, 3)) * sigma).astype(np.float32)
+    out = rng.random(n) >= inlier_frac
+    dst[out] = rng.random((int(out.sum()), 3), dtype=np.float32)
+    return dst.astype(np.float32), src, T_ref, ~out
+
+
+def frobenius(Ta, Tb):
+    return float(np.linalg.norm(np.asarray(Ta, np.float64) - np.asarray(Tb, np.float64)))

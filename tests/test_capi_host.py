@@ -1,0 +1,139 @@
+"""CPU-side checks of the product library (no GPU, no compute kernels):
+  * libcilantro_b200.so loads and exports every symbol include/cilantro_b200.h declares;
+  * without a device the library refuses to create a context (no CPU fallback);
+  * the host-only O(1) solves agree with the oracle's independent implementations.
+"""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cilantro_b200 import synth
+from conftest import frob
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "cilantro_b200.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(cb_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol(cb):
+    lib = cb.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 35
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, f"declared in include/cilantro_b200.h but not exported: {missing}"
+    assert sorted(cb.EXPORTED) == declared, "capi.EXPORTED is out of sync with the header"
+    assert b"sm_100a" in lib.cb_version()
+
+
+def test_no_cpu_fallback_without_device(cb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; covered by the gpu tests")
+    with pytest.raises(cb.CbError) as e:
+        cb.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_missing_library_fails_loudly(cb, monkeypatch):
+    monkeypatch.setattr(cb, "_lib", None)
+    monkeypatch.setattr(cb, "LIB_PATH", "/nonexistent/libcilantro_b200.so")
+    with pytest.raises(cb.CbError):
+        cb.lib()
+
+
+def _moments(dst, src):
+    d, s = dst.astype(np.float64), src.astype(np.float64)
+    out = np.zeros(16)
+    out[0] = d.shape[0]
+    out[1:4] = d.sum(0)
+    out[4:7] = s.sum(0)
+    out[7:] = (d.T @ s).reshape(-1)
+    return out
+
+
+def test_solve_kabsch_moments_matches_oracle(cb, orc):
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(3, 4000))
+        src = rng.random((n, 3), dtype=np.float32)
+        T = synth.rigid_from_axis_angle(rng.normal(size=3), rng.uniform(-1, 1), rng.normal(size=3) * 0.3)
+        dst = synth.apply(T, src) + (rng.normal(size=(n, 3)) * 1e-3).astype(np.float32)
+        if trial % 5 == 0:
+            dst = dst * np.float32([1, 1, -1])  # forces the reflection branch
+        Tp, okp = cb.solve_kabsch_moments(_moments(dst, src))
+        To, oko = orc.kabsch(dst, src, accum_double=True)
+        assert okp == oko
+        # the mirrored case is ill-conditioned (the fix flips the axis of the smallest singular value;
+        # the oracle rounds sigma to fp32 like the reference, the product keeps double)
+        assert frob(Tp, To) < (5e-5 if trial % 5 == 0 else 2e-6), (trial, frob(Tp, To))
+        assert abs(np.linalg.det(Tp[:, :3].astype(np.float64)) - 1) < 1e-5
+    # 3 points (RANSAC sample): rank-deficient covariance
+    src = rng.random((3, 3), dtype=np.float32)
+    dst = synth.apply(T, src)
+    Tp, okp = cb.solve_kabsch_moments(_moments(dst, src))
+    To, _ = orc.kabsch(dst, src, accum_double=True)
+    assert okp and frob(Tp, To) < 5e-6
+    assert np.abs(synth.apply(Tp, src) - dst).max() < 1e-5
+    # no pairs -> identity, false (transform_estimation.hpp:20-23)
+    Tp, okp = cb.solve_kabsch_moments(np.zeros(16))
+    assert not okp and frob(Tp, orc.identity()) == 0
+
+
+def test_solve_gauss_newton_matches_oracle(cb, orc):
+    rng = np.random.default_rng(1)
+    dst, src, nrm, T_ref = synth.icp_pair(3000, seed=8, noise=0.0005, with_normals=True)
+    q = synth.apply(T_ref, src)  # almost aligned
+    idx = np.arange(3000)
+    for w_pt, w_pl in ((0.0, 1.0), (0.3, 1.0), (1.0, 0.0)):
+        # build the normal equations exactly as the kernel does (double precision)
+        d = dst.astype(np.float64)
+        s = q.astype(np.float64)
+        v, e = d + s, d - s
+        A = np.zeros((6, 6))
+        b = np.zeros(6)
+        if w_pl > 0:
+            a = np.hstack([np.cross(v, nrm.astype(np.float64)), nrm.astype(np.float64)])
+            r = (nrm.astype(np.float64) * e).sum(1)
+            A += w_pl * a.T @ a
+            b += w_pl * a.T @ r
+        if w_pt > 0:
+            for i in range(3000):
+                vx = np.array([[0, -v[i, 2], v[i, 1]], [v[i, 2], 0, -v[i, 0]], [-v[i, 1], v[i, 0], 0]])
+                E = np.vstack([vx, np.eye(3)])  # eq_vecs, transform_estimation.hpp:306-316
+                A += w_pt * E @ E.T
+                b += w_pt * E @ e[i]
+        sums = np.zeros(28)
+        sums[0] = 3000
+        sums[1:22] = A[np.triu_indices(6)]
+        sums[22:] = b
+        Tp, dn = cb.solve_gauss_newton(sums)
+        To, _ = orc.estimate_combined(dst, nrm, q, idx, idx, w_pt, w_pl, 1, 1e-5, accum_double=True)
+        assert frob(Tp, To) < 2e-6, (w_pt, w_pl, frob(Tp, To))
+        assert dn > 0
+
+
+def test_solve_rotation_and_compose(cb, orc):
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        R = synth.rigid_from_axis_angle(rng.normal(size=3), rng.uniform(-3, 3), [0, 0, 0])[:, :3]
+        noisy = (R + 1e-4 * rng.normal(size=(3, 3))).astype(np.float32)
+        assert np.abs(cb.solve_rotation(noisy) - orc.rotation(noisy)).max() < 1e-6
+    A = synth.rigid_from_axis_angle([1, 0, 0], 0.3, [1, 2, 3]).astype(np.float32)
+    B = synth.rigid_from_axis_angle([0, 1, 0], -0.2, [-1, 0, 4]).astype(np.float32)
+    AB = cb.compose(A, B)
+    p = rng.random((10, 3), dtype=np.float32)
+    assert np.abs(synth.apply(AB, p) - synth.apply(A, synth.apply(B, p))).max() < 1e-5
+
+
+def test_kmeans_seed_indices_host(cb, orc):
+    assert np.array_equal(cb.kmeans_seed_indices(5000, 100, 42), orc.kmeans_seed_indices(5000, 100, 42))
