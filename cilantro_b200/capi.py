@@ -7,6 +7,7 @@ CUDA device is present.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -130,9 +131,15 @@ class Context:
         _check(lib().cb_context_create(C.c_int(device), C.byref(h)))
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()  # clouds / icp objects must be destroyed before the context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def close(self):
         if self.h:
+            for child in list(self._children):
+                child.close()
             lib().cb_context_destroy(self.h)
             self.h = None
 
@@ -194,6 +201,7 @@ class Cloud:
                                          C.byref(h)))
             self.n = xyz.shape[0]
         self.h = h
+        ctx._adopt(self)
 
     def close(self):
         if self.h:
@@ -276,6 +284,7 @@ class Icp:
         h = C.c_void_p()
         _check(lib().cb_icp_create(ctx.h, dst.h, src.h, C.byref(h)))
         self.h = h
+        ctx._adopt(self)
 
     def close(self):
         if self.h:
@@ -301,6 +310,7 @@ class Icp:
             "converged": bool(res.converged),
             "num_corr": int(res.num_corr),
             "gpu_ms_total": float(res.gpu_ms_total),
+            "gpu_ms_search": float(res.gpu_ms_search),
             "iter_ms": times[:max(n, 0)],
             "kernel_launches": int(res.kernel_launches),
         }

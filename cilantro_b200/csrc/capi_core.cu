@@ -62,6 +62,7 @@ struct cb_icp {
   int* d_nn_pos = nullptr;  // per sorted src point: sorted dst position of its match, -1 none
   float* d_nn_d2 = nullptr;
   bool nn_valid = false;
+  double search_ms = 0;  // CUDA-event time of the fused search+accumulate kernels of the last estimate()
   std::vector<cudaEvent_t> events;
   std::vector<double> iter_ms;
 };
@@ -404,8 +405,15 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   double sums[kMaxValues];
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
     CB_TRY(icp_fill_args(icp, prm, T, nullptr, &a));
+    CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
+    CB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     CB_TRY(fetch_result(ctx, kP2PValues, true, sums));
+    {
+      float ms = 0.f;
+      CB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      icp->search_ms += ms;
+    }
     kabsch_from_moments(sums, Titer);
     *n_corr = sums[0];
     icp->nn_valid = true;
@@ -425,9 +433,14 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
     CB_TRY(icp_fill_args(icp, prm, T, Tin, &a));
     const bool search = (it == 0);
     // the first pass always runs (it is also the correspondence search of this ICP iteration)
+    if (search) CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
+    if (search) CB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     CB_TRY(fetch_result(ctx, kCombinedValues, true, sums));
     if (search) {
+      float ms = 0.f;
+      CB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+      icp->search_ms += ms;
       *n_corr = sums[0];
       icp->nn_valid = true;
     }
@@ -470,6 +483,7 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   float last_delta = INFINITY;
   double n_corr = 0;
   icp->nn_valid = false;
+  icp->search_ms = 0;
   while (iters < max_iter) {  // icp_base.hpp:76-84
     if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
     CB_CUDA(cudaEventRecord(icp->events[2 * iters], ctx->stream));
@@ -499,7 +513,7 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   res->converged = last_delta < prm->tol;
   res->num_corr = (uint64_t)(n_corr + 0.5);
   res->gpu_ms_total = total;
-  res->gpu_ms_search = total;
+  res->gpu_ms_search = icp->search_ms;
   res->kernel_launches = ctx->launches - launches0;
   return CB_OK;
 }

@@ -151,7 +151,7 @@ def test_icp_1m_recovers_reference_pose(cb, ctx):
     res = icp.estimate(metric="p2p", max_iter=15, tol=0.0, max_d2=np.float32(0.02**2))
     assert res["iterations"] == 15
     assert res["num_corr"] == 1_000_000
-    assert frob(res["T"], T_ref) < 2e-5
+    assert frob(res["T"], T_ref) < 2e-5, frob(res["T"], T_ref)
     again = icp.estimate(metric="p2p", max_iter=1, tol=0.0, max_d2=np.float32(0.02**2), T_init=res["T"])
     assert frob(again["T"], res["T"]) < 1e-6
 
