@@ -33,18 +33,22 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build an experimental variant (e.g. defines=["CB_ICP_MIN_BLOCKS=3"], out="x.so")."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-ccbin", "g++", "-o", LIB] + sources() + [
-        "-ldl"]
+    target = LIB if out is None else os.path.join(HERE, out)
+    cmd = [nvcc] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + [
+        "-ccbin", "g++", "-o", target] + sources() + ["-ldl"]
     env = dict(os.environ)
     env.pop("CXX", None)  # the image exports a wrapper g++ without OpenMP specs; use the PATH compiler
     env.pop("CC", None)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, out=outs[0] if outs else None))

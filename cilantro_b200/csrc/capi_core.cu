@@ -23,12 +23,28 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
-int ensure_scratch(cb_context* ctx, size_t partial_doubles) {
-  if (ctx->partials_cap >= partial_doubles) return CB_OK;
-  if (ctx->d_partials) CB_CUDA(cudaFree(ctx->d_partials));
-  size_t cap = std::max<size_t>(partial_doubles, 4096 * 32);
-  CB_CUDA(cudaMalloc(&ctx->d_partials, cap * sizeof(double)));
-  ctx->partials_cap = cap;
+int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out) {
+  const size_t groups = ((size_t)blocks + kReduceGroup - 1) / kReduceGroup;
+  const size_t need = ((size_t)blocks + groups) * (size_t)nv;
+  if (ctx->partials_cap < need) {
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_partials) CB_CUDA(cudaFree(ctx->d_partials));
+    const size_t cap = std::max<size_t>(need, (size_t)8192 * 32);
+    CB_CUDA(cudaMalloc(&ctx->d_partials, cap * sizeof(double)));
+    ctx->partials_cap = cap;
+  }
+  if (ctx->counter_cap < groups + 1) {
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_counter) CB_CUDA(cudaFree(ctx->d_counter));
+    const size_t cap = std::max<size_t>(groups + 1, 4096);
+    CB_CUDA(cudaMalloc(&ctx->d_counter, cap * sizeof(unsigned int)));
+    CB_CUDA(cudaMemset(ctx->d_counter, 0, cap * sizeof(unsigned int)));
+    ctx->counter_cap = cap;
+  }
+  out->partials = ctx->d_partials;
+  out->gpartials = ctx->d_partials + (size_t)blocks * nv;
+  out->counters = ctx->d_counter;
+  out->result = ctx->d_result;
   return CB_OK;
 }
 
@@ -61,7 +77,10 @@ struct cb_icp {
   float src_mean[3] = {0, 0, 0};
   int* d_nn_pos = nullptr;  // per sorted src point: sorted dst position of its match, -1 none
   float* d_nn_d2 = nullptr;
-  bool nn_valid = false;
+  bool nn_valid = false;    // a search has run; T_search / max_d2_search describe it
+  bool nn_stored = false;   // d_nn_pos / d_nn_d2 hold that search's per-query result
+  float T_search[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  float max_d2_search = 0.f;
   double search_ms = 0;  // CUDA-event time of the fused search+accumulate kernels of the last estimate()
   std::vector<cudaEvent_t> events;
   std::vector<double> iter_ms;
@@ -94,8 +113,6 @@ int cb_context_create(int device, cb_context** out) {
   ctx->hbm_bytes = prop.totalGlobalMem;
   snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
   CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CB_CUDA(cudaMalloc(&ctx->d_counter, sizeof(unsigned int)));
-  CB_CUDA(cudaMemset(ctx->d_counter, 0, sizeof(unsigned int)));
   CB_CUDA(cudaMalloc(&ctx->d_result, 64 * sizeof(double)));
   CB_CUDA(cudaMemset(ctx->d_result, 0, 64 * sizeof(double)));
   CB_CUDA(cudaMallocHost(&ctx->h_result, 64 * sizeof(double)));
@@ -377,7 +394,8 @@ void cb_icp_destroy(cb_icp* icp) {
   delete icp;
 }
 
-static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, const float* Tin, IcpArgs* a) {
+static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, const float* Tin, bool store,
+                         IcpArgs* a) {
   std::memset(a, 0, sizeof(*a));
   a->dst = grid_view(icp->dst);
   a->src_pts = icp->src->d_pts;
@@ -392,8 +410,13 @@ static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, 
   float smt[3];
   apply_point(T, icp->src_mean, smt);  // this->transform_ * src_mean_  (:189/:196)
   for (int r = 0; r < 3; r++) a->sm[r] = smt[r];
-  a->nn_pos = icp->d_nn_pos;
-  a->nn_d2 = icp->d_nn_d2;
+  // The per-query result is only written when something will read it back (inner Gauss-Newton
+  // iterations >= 2, cb_icp_accumulate); cb_icp_correspondences re-runs the search otherwise.
+  a->nn_pos = store ? icp->d_nn_pos : nullptr;
+  a->nn_d2 = store ? icp->d_nn_d2 : nullptr;
+  std::memcpy(icp->T_search, T, sizeof(icp->T_search));
+  icp->max_d2_search = prm->max_d2;
+  icp->nn_stored = store;
   return CB_OK;
 }
 
@@ -404,7 +427,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   IcpArgs a;
   double sums[kMaxValues];
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
-    CB_TRY(icp_fill_args(icp, prm, T, nullptr, &a));
+    CB_TRY(icp_fill_args(icp, prm, T, nullptr, false, &a));
     CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
     CB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -430,7 +453,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   const int max_opt = std::max(prm->max_opt_iter, 0);
   bool any_pass = false;
   for (int it = 0; it < std::max(max_opt, 1); ++it) {
-    CB_TRY(icp_fill_args(icp, prm, T, Tin, &a));
+    CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1, &a));
     const bool search = (it == 0);
     // the first pass always runs (it is also the correspondence search of this ICP iteration)
     if (search) CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -530,7 +553,7 @@ int cb_icp_accumulate(cb_icp* icp, const cb_icp_params* prm, const float* T12, d
   cb_context* ctx = icp->ctx;
   CB_CUDA(cudaSetDevice(ctx->device));
   IcpArgs a;
-  CB_TRY(icp_fill_args(icp, prm, T12, nullptr, &a));
+  CB_TRY(icp_fill_args(icp, prm, T12, nullptr, true, &a));
   double tmp[kMaxValues];
   int nv;
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
@@ -556,6 +579,19 @@ int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_s
   const size_t ns = icp->src->n;
   *count = 0;
   if (ns == 0) return CB_OK;
+  if (!icp->nn_stored) {  // re-run the last search, this time keeping the per-query result
+    IcpArgs a{};
+    a.dst = grid_view(icp->dst);
+    a.src_pts = icp->src->d_pts;
+    a.n_src = (uint32_t)ns;
+    a.T = to_rigid(icp->T_search);
+    a.Tin = to_rigid(nullptr);
+    a.max_d2 = icp->max_d2_search;
+    a.nn_pos = icp->d_nn_pos;
+    a.nn_d2 = icp->d_nn_d2;
+    CB_TRY(launch_icp_pass(ctx, a, kModeKnn, true, false, false));
+    icp->nn_stored = true;
+  }
   // nn_pos is indexed by sorted src position and holds sorted dst positions: translate on the host
   std::vector<int> pos(ns);
   std::vector<float> nd2(ns);

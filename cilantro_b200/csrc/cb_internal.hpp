@@ -39,6 +39,17 @@ void set_error(const char* fmt, ...);
 // Uniform grid over a cloud. Points are stored cell-sorted as float4 (x, y, z, original index bits);
 // cells are x-major: id = (z * ny + y) * nx + x, so the three x-neighbours of a row are one
 // contiguous range of the sorted array.
+constexpr int kReduceBlock = 256;  // every kernel using grid_reduce (reduce.cuh) launches with this block size
+constexpr int kReduceGroup = 64;   // blocks per first-level reduction group
+
+// Device scratch of the two-level grid reduction (reduce.cuh), owned by the context.
+struct ReduceScratch {
+  double* partials;        // [gridDim.x][NV]   one row per block
+  double* gpartials;       // [ngroups][NV]     one row per group of kReduceGroup blocks
+  unsigned int* counters;  // [ngroups + 1]     tickets; zero on entry, reset by their last user
+  double* result;          // [NV]
+};
+
 struct GridView {
   const float4* pts;           // n, cell-sorted; .w = __int_as_float(original index)
   const float4* nrm;           // n, same order (or nullptr)
@@ -63,7 +74,8 @@ struct cb_context {
   // reduction scratch: per-block partials -> last block -> result
   double* d_partials = nullptr;
   size_t partials_cap = 0;  // in doubles
-  unsigned int* d_counter = nullptr;
+  unsigned int* d_counter = nullptr;  // ticket counters of the grid reduction (zero between launches)
+  size_t counter_cap = 0;
   double* d_result = nullptr;  // 64 doubles
   double* h_result = nullptr;  // pinned, 64 doubles
   void* d_flush = nullptr;
@@ -94,7 +106,8 @@ namespace cb {
 
 int ensure_index(cb_cloud* c);
 GridView grid_view(const cb_cloud* c);
-int ensure_scratch(cb_context* ctx, size_t partial_doubles);
+// Scratch for a grid_reduce over `blocks` blocks of `nv` values each (grown on demand).
+int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out);
 
 // nccl_dyn.cpp
 int nccl_unique_id(void* out128);

@@ -348,7 +348,9 @@ int ensure_index(cb_cloud* c) {
       size_t tot = 1;
       bool ok = true;
       for (int a = 0; a < 3; a++) {
-        double d = std::floor(ext[a] / h) + 1.0;
+        // one empty margin cell on each side: queries up to a cell outside the bounding box (every
+        // ICP run has them along the faces) stay on the pooled "inside the grid" search path
+        double d = std::floor(ext[a] / h) + 3.0;
         if (d > kMaxDim) ok = false;
         dims[a] = (int)std::min<double>(d, kMaxDim);
         tot *= (size_t)dims[a];
@@ -356,9 +358,9 @@ int ensure_index(cb_cloud* c) {
       if (ok && tot <= cell_cap) break;
       h *= 1.26;
     }
-    gp.ox = mn[0];
-    gp.oy = mn[1];
-    gp.oz = mn[2];
+    gp.ox = (float)((double)mn[0] - h);
+    gp.oy = (float)((double)mn[1] - h);
+    gp.oz = (float)((double)mn[2] - h);
     gp.inv_h = (float)(1.0 / h);
     gp.nx = dims[0];
     gp.ny = dims[1];

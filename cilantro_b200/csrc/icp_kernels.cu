@@ -14,6 +14,7 @@
 // correspondence list is only materialised when a caller asks for it.
 #include "icp_kernels.cuh"
 #include "reduce.cuh"
+#include "warp_search.cuh"
 #include <algorithm>
 
 namespace cb {
@@ -24,22 +25,60 @@ constexpr int kBlock = kReduceBlock;
 
 __device__ __forceinline__ constexpr int ut(int r, int c) { return r * 6 - (r * (r - 1)) / 2 + (c - r); }
 
+// cp.async.bulk.prefetch.L2: one instruction asks the memory system to pull `bytes` (multiple of 16,
+// 16-byte aligned address) from HBM into L2 without occupying registers or a scoreboard slot.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+#ifndef CB_ICP_MIN_BLOCKS
+#define CB_ICP_MIN_BLOCKS 4
+#endif
+
 template <int MODE, bool SEARCH>
-__global__ void __launch_bounds__(kBlock) icp_pass_kernel(const IcpArgs a, const bool has_pt, const bool has_pl) {
+__global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(const IcpArgs a, const bool has_pt, const bool has_pl) {
   constexpr int NV = (MODE == kModeP2P) ? kP2PValues : (MODE == kModeCombined ? kCombinedValues : 1);
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) acc[i] = 0.0;
 
-  const uint32_t stride = gridDim.x * blockDim.x;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n_src; i += stride) {
-    const float4 s = __ldg(a.src_pts + i);
-    float qx, qy, qz;
-    apply_rigid(a.T, s.x, s.y, s.z, qx, qy, qz);
-
-    int pos;
-    if (SEARCH) {
-      const Best best = grid_nearest(a.dst, qx, qy, qz, a.max_d2);
+  // ONE query per thread: the moment accumulators are dead during the search, so the search runs at
+  // a low register count. Blocks own 256 consecutive queries of the cell-sorted source cloud, i.e. a
+  // compact spatial neighbourhood (L1 reuse of the reference cells).
+  __shared__ WarpSearchSmem wsm[SEARCH ? kBlock / 32 : 1];
+  if (SEARCH && threadIdx.x == 0 && a.dst.n > 0) {
+    // Software prefetch of the reference arrays into L2, a fixed number of blocks ahead of the
+    // consumer front. Both clouds are cell-sorted x-major in (nearly) the same frame, so block b of
+    // the query cloud reads the reference arrays around the fraction b / gridDim.x; the bulk
+    // prefetch turns the first-touch DRAM latency of the dependent cell-table -> point loads into an
+    // L2 hit. A hint only: DRAM traffic and results are unchanged.
+    const uint32_t nb = gridDim.x, D = a.prefetch_blocks;
+    const uint32_t n_dst = a.dst.n;
+    const uint32_t ncells = (uint32_t)a.dst.nx * (uint32_t)a.dst.ny * (uint32_t)a.dst.nz;
+    auto prefetch_slice = [&](uint32_t blk) {
+      const uint32_t lo = (uint32_t)(((unsigned long long)blk * n_dst) / nb);
+      const uint32_t hi = (uint32_t)(((unsigned long long)(blk + 1) * n_dst) / nb);
+      if (hi > lo) {
+        bulk_prefetch_l2(a.dst.pts + lo, (hi - lo) * 16u);
+        if (MODE == kModeCombined && a.dst.nrm) bulk_prefetch_l2(a.dst.nrm + lo, (hi - lo) * 16u);
+      }
+      const uint32_t clo = (uint32_t)(((unsigned long long)blk * ncells) / nb) & ~3u;
+      const uint32_t chi = min(ncells, ((uint32_t)(((unsigned long long)(blk + 1) * ncells) / nb) + 3u) & ~3u);
+      if (chi > clo + 3u) bulk_prefetch_l2(a.dst.cell_start + clo, ((chi - clo) & ~3u) * 4u);
+    };
+    if (blockIdx.x + D < nb) prefetch_slice(blockIdx.x + D);
+    if (blockIdx.x < D) prefetch_slice(blockIdx.x);  // the first D blocks have nobody ahead of them
+  }
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < a.n_src;
+  const float4 s = active ? __ldg(a.src_pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float qx, qy, qz;
+  apply_rigid(a.T, s.x, s.y, s.z, qx, qy, qz);
+  int pos = -1;
+  if (SEARCH) {
+    // every lane of the warp takes part in the pooled search (inactive tail lanes contribute no work)
+    const Best best = warp_grid_nearest(a.dst, wsm[threadIdx.x >> 5], active, qx, qy, qz, a.max_d2);
+    if (active) {
       pos = (best.idx >= 0 && best.d2 < a.max_d2) ? best.pos : -1;
       if (a.nn_pos) a.nn_pos[i] = pos;
       if (a.nn_d2) a.nn_d2[i] = best.d2;
@@ -48,11 +87,11 @@ __global__ void __launch_bounds__(kBlock) icp_pass_kernel(const IcpArgs a, const
         if (a.out_idx) a.out_idx[oi] = (pos >= 0) ? best.idx : -1;
         if (a.out_d2) a.out_d2[oi] = (pos >= 0) ? best.d2 : a.max_d2;
       }
-    } else {
-      pos = a.nn_pos[i];
     }
-    if (MODE == kModeKnn || pos < 0) continue;
-
+  } else if (active) {
+    pos = a.nn_pos[i];
+  }
+  if (MODE != kModeKnn && pos >= 0) {
     const float4 dp = __ldg(a.dst.pts + pos);
     if constexpr (MODE == kModeP2P) {
       const double dx = dp.x, dy = dp.y, dz = dp.z, x = qx, y = qy, z = qz;
@@ -128,7 +167,7 @@ __global__ void __launch_bounds__(kBlock) icp_pass_kernel(const IcpArgs a, const
       }
     }
   }
-  if (MODE != kModeKnn) grid_reduce<NV>(acc, a.partials, a.counter, a.result);
+  if (MODE != kModeKnn) grid_reduce<NV>(acc, a.rs);
 }
 
 __global__ void __launch_bounds__(kBlock) residual_kernel(const GridView dst, const float4* __restrict__ src_pts,
@@ -194,14 +233,18 @@ int icp_grid_blocks(const cb_context* ctx) {
 
 int launch_icp_pass(cb_context* ctx, const IcpArgs& a, int mode, bool search, bool has_pt, bool has_pl) {
   if (a.n_src == 0 && mode == kModeKnn) return CB_OK;
-  int blocks = icp_grid_blocks(ctx);
-  const int need = (int)((a.n_src + kBlock - 1) / kBlock);
-  blocks = std::max(1, std::min(blocks, need));
-  CB_TRY(ensure_scratch(ctx, (size_t)blocks * kMaxValues));
+  // one query per thread; the hardware block scheduler balances the (variable-cost) searches
+  const int blocks = std::max(1, (int)((a.n_src + kBlock - 1) / kBlock));
   IcpArgs args = a;
-  args.partials = ctx->d_partials;
-  args.counter = ctx->d_counter;
-  args.result = ctx->d_result;
+  CB_TRY(get_reduce_scratch(ctx, blocks, kMaxValues, &args.rs));
+  {
+    // ~2 waves of resident blocks; CB_PREFETCH_BLOCKS overrides it for experiments
+    static const int env_pf = [] {
+      const char* e = getenv("CB_PREFETCH_BLOCKS");
+      return e ? atoi(e) : -1;
+    }();
+    args.prefetch_blocks = env_pf >= 0 ? (uint32_t)env_pf : (uint32_t)(2 * ctx->sm_count * CB_ICP_MIN_BLOCKS);
+  }
   if (mode == kModeKnn) {
     icp_pass_kernel<kModeKnn, true><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
   } else if (mode == kModeP2P) {

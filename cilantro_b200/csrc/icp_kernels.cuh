@@ -23,6 +23,7 @@ struct IcpArgs {
   Rigid T;       // current estimate: q = T * s  (the search AND the estimator use this q)
   Rigid Tin;     // inner Gauss-Newton transform (identity in the fused first pass)
   float max_d2;
+  uint32_t prefetch_blocks;  // L2 prefetch look-ahead of the search kernel, in blocks (set by the launcher)
   float w_pt, w_pl;
   float dm[3];   // dst_mean_
   float sm[3];   // transform_ * src_mean_
@@ -33,9 +34,7 @@ struct IcpArgs {
   int* out_idx;   // original dst index or -1
   float* out_d2;
   // reduction scratch
-  double* partials;       // gridDim.x * kMaxValues
-  unsigned int* counter;  // zero on entry; reset to zero by the last block
-  double* result;         // kMaxValues
+  ReduceScratch rs;  // grid-reduction scratch (set by the launcher)
 };
 
 // One pass over the query cloud. kSearch = false re-uses nn_pos from a previous pass (inner

@@ -56,8 +56,9 @@ __host__ __device__ __forceinline__ float cell_coord(float x, float o, float inv
 
 struct Best {
   float d2;
-  int idx;  // original reference index, -1 = none
-  int pos;  // position in the cell-sorted array
+  int idx;   // original reference index, -1 = none
+  int pos;   // position in the cell-sorted array
+  bool tie;  // fast pass only: some candidate had d2 bit-equal to the running best
 };
 
 constexpr float kCellMargin = 0.0009765625f;  // 2^-10 cell
@@ -65,20 +66,55 @@ constexpr float kCellMargin = 0.0009765625f;  // 2^-10 cell
 __constant__ signed char kRowDy[9] = {0, -1, 1, 0, 0, -1, 1, -1, 1};
 __constant__ signed char kRowDz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
 
+// kExact = true resolves exact ties on the original index inside the loop. kExact = false (the fast
+// pass) keeps the first strictly smaller candidate and only RECORDS that a bit-equal distance was
+// seen; grid_nearest() then repeats the search with kExact = true for that (very rare) query.
+template <bool kExact>
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t b, uint32_t e, float qx,
                                            float qy, float qz, Best& best) {
+  if (kExact) {
 #pragma unroll 2
-  for (uint32_t j = b; j < e; ++j) {
-    const float4 p = __ldg(pts + j);
-    const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-    float r = __fmul_rn(dx, dx);
-    r = __fadd_rn(r, __fmul_rn(dy, dy));
-    r = __fadd_rn(r, __fmul_rn(dz, dz));
-    const int pi = __float_as_int(p.w);
-    if (r < best.d2 || (r == best.d2 && pi < best.idx)) {
-      best.d2 = r;
-      best.idx = pi;
-      best.pos = (int)j;
+    for (uint32_t j = b; j < e; ++j) {
+      const float4 p = __ldg(pts + j);
+      const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+      float r = __fmul_rn(dx, dx);
+      r = __fadd_rn(r, __fmul_rn(dy, dy));
+      r = __fadd_rn(r, __fmul_rn(dz, dz));
+      const int pi = __float_as_int(p.w);
+      if (r < best.d2 || (r == best.d2 && pi < best.idx)) {
+        best.d2 = r;
+        best.idx = pi;
+        best.pos = (int)j;
+      }
+    }
+  } else {
+    // The scan is a chain of load -> use steps; ncu showed ~25 such waits per warp at ~900 cycles
+    // each (long scoreboard = 64 % of warp residency). Batches of kW candidates put kW loads in
+    // flight per wait; slots past the end of the range are predicated off (no padded arithmetic —
+    // a padded variant doubled the instruction count and was slower).
+    constexpr int kW = 4;
+    auto eval = [&](const float4& p, uint32_t j) {
+      const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+      float r = __fmul_rn(dx, dx);
+      r = __fadd_rn(r, __fmul_rn(dy, dy));
+      r = __fadd_rn(r, __fmul_rn(dz, dz));
+      if (r < best.d2) {
+        best.d2 = r;
+        best.pos = (int)j;
+      } else if (r == best.d2) {
+        best.tie = true;
+      }
+    };
+    for (uint32_t j = b; j < e; j += kW) {
+      float4 p[kW];
+      p[0] = __ldg(pts + j);
+#pragma unroll
+      for (int u = 1; u < kW; u++)
+        if (j + u < e) p[u] = __ldg(pts + j + u);
+      eval(p[0], j);
+#pragma unroll
+      for (int u = 1; u < kW; u++)
+        if (j + u < e) eval(p[u], j + u);
     }
   }
 }
@@ -94,11 +130,13 @@ __device__ __forceinline__ float slab_gap(float f, int c, int r) {
 }
 
 // Exact nearest neighbour of (qx,qy,qz) among the grid's points with d2 < max_d2.
-__device__ __forceinline__ Best grid_nearest(const GridView& g, float qx, float qy, float qz, float max_d2) {
+template <bool kExact>
+__device__ __forceinline__ Best grid_nearest_impl(const GridView& g, float qx, float qy, float qz, float max_d2) {
   Best best;
   best.d2 = max_d2;
   best.idx = -1;
   best.pos = -1;
+  best.tie = false;
   if (g.n == 0) return best;
 
   const float fx = cell_coord(qx, g.ox, g.inv_h);
@@ -114,7 +152,46 @@ __device__ __forceinline__ Best grid_nearest(const GridView& g, float qx, float 
   k0 = max(k0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
 
   int k = k0;
-  if (k0 <= 1) {
+  if (k0 == 0) {
+    // Query cell inside the grid (the common case). Shells 0 and 1: all 20 cell-table entries are
+    // requested up front (independent loads, one latency), then the cells are visited from the most
+    // to the least promising: own cell, its two x-neighbours, the 4 face rows, the 4 corner rows,
+    // each skipped when its lower bound already exceeds the best distance.
+    const int xm = max(cx - 1, 0), xp = min(cx + 1, g.nx - 1);
+    const uint32_t cbase = ((uint32_t)cz * (uint32_t)g.ny + (uint32_t)cy) * (uint32_t)g.nx;
+    const uint32_t s0 = __ldg(g.cell_start + cbase + xm), s1 = __ldg(g.cell_start + cbase + cx);
+    const uint32_t s2 = __ldg(g.cell_start + cbase + cx + 1), s3 = __ldg(g.cell_start + cbase + xp + 1);
+    constexpr int kDy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};  // 4 face rows, then 4 corner rows
+    constexpr int kDz[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+    uint32_t rb[8], re[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int ry = cy + kDy[t], rz = cz + kDz[t];
+      const bool valid = (ry >= 0) & (ry < g.ny) & (rz >= 0) & (rz < g.nz);
+      const uint32_t base = valid ? ((uint32_t)rz * (uint32_t)g.ny + (uint32_t)ry) * (uint32_t)g.nx : cbase;
+      const uint32_t b = __ldg(g.cell_start + base + xm), e = __ldg(g.cell_start + base + xp + 1);
+      rb[t] = valid ? b : 0u;
+      re[t] = valid ? e : 0u;
+    }
+    scan_range<kExact>(g.pts, s1, s2, qx, qy, qz, best);
+    {
+      const float gl = slab_gap(fx, cx, cx - 1), gr = slab_gap(fx, cx, cx + 1);
+      if (gl * gl * hs2 < best.d2) scan_range<kExact>(g.pts, s0, s1, qx, qy, qz, best);
+      if (gr * gr * hs2 < best.d2) scan_range<kExact>(g.pts, s2, s3, qx, qy, qz, best);
+    }
+    {
+      const float gym = slab_gap(fy, cy, cy - 1), gyp = slab_gap(fy, cy, cy + 1);
+      const float gzm = slab_gap(fz, cz, cz - 1), gzp = slab_gap(fz, cz, cz + 1);
+      const float gy2[3] = {gym * gym, 0.f, gyp * gyp};
+      const float gz2[3] = {gzm * gzm, 0.f, gzp * gzp};
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const float lb = (gy2[kDy[t] + 1] + gz2[kDz[t] + 1]) * hs2;
+        if (lb < best.d2 && rb[t] < re[t]) scan_range<kExact>(g.pts, rb[t], re[t], qx, qy, qz, best);
+      }
+    }
+    k = 2;
+  } else if (k0 == 1) {
     // Shells 0 and 1 together: 9 rows of up to 3 contiguous cells. Centre row first so that the
     // bound is tight before the 8 neighbour rows are tested for pruning.
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
@@ -128,7 +205,7 @@ __device__ __forceinline__ Best grid_nearest(const GridView& g, float qx, float 
         if ((gy * gy + gz * gz) * hs2 >= best.d2) continue;
         const uint32_t base = ((uint32_t)rz * (uint32_t)g.ny + (uint32_t)ry) * (uint32_t)g.nx;
         const uint32_t b = __ldg(g.cell_start + base + x0), e = __ldg(g.cell_start + base + x1 + 1);
-        scan_range(g.pts, b, e, qx, qy, qz, best);
+        scan_range<kExact>(g.pts, b, e, qx, qy, qz, best);
       }
     }
     k = 2;
@@ -173,27 +250,34 @@ __device__ __forceinline__ Best grid_nearest(const GridView& g, float qx, float 
         if (zshell || (ry - cy == k) || (cy - ry == k)) {
           if (x0 <= x1) {
             const uint32_t b = __ldg(g.cell_start + base + x0), e = __ldg(g.cell_start + base + x1 + 1);
-            scan_range(g.pts, b, e, qx, qy, qz, best);
+            scan_range<kExact>(g.pts, b, e, qx, qy, qz, best);
           }
         } else {
           if (xl >= 0 && xl < g.nx) {
             const float gx = slab_gap(fx, cx, xl);
             if ((gx * gx + gyz2) * hs2 < best.d2) {
               const uint32_t b = __ldg(g.cell_start + base + xl), e = __ldg(g.cell_start + base + xl + 1);
-              scan_range(g.pts, b, e, qx, qy, qz, best);
+              scan_range<kExact>(g.pts, b, e, qx, qy, qz, best);
             }
           }
           if (xr >= 0 && xr < g.nx) {
             const float gx = slab_gap(fx, cx, xr);
             if ((gx * gx + gyz2) * hs2 < best.d2) {
               const uint32_t b = __ldg(g.cell_start + base + xr), e = __ldg(g.cell_start + base + xr + 1);
-              scan_range(g.pts, b, e, qx, qy, qz, best);
+              scan_range<kExact>(g.pts, b, e, qx, qy, qz, best);
             }
           }
         }
       }
     }
   }
+  if (!kExact && best.pos >= 0) best.idx = __float_as_int(__ldg(&g.pts[best.pos].w));
+  return best;
+}
+
+__device__ __forceinline__ Best grid_nearest(const GridView& g, float qx, float qy, float qz, float max_d2) {
+  Best best = grid_nearest_impl<false>(g, qx, qy, qz, max_d2);
+  if (best.tie) best = grid_nearest_impl<true>(g, qx, qy, qz, max_d2);
   return best;
 }
 

@@ -99,8 +99,7 @@ __global__ void ransac_residual_kernel(const float* __restrict__ dst, const floa
 // {n, sum d (3), sum s (3), sum d s^T (9)} over pairs with residual <= thresh.
 __global__ void __launch_bounds__(kReduceBlock) inlier_moments_kernel(const float* __restrict__ dst,
                                                                       const float* __restrict__ src, size_t n,
-                                                                      const Rigid T, float x_max, double* partials,
-                                                                      unsigned int* counter, double* result) {
+                                                                      const Rigid T, float x_max, const ReduceScratch rs) {
   double acc[16];
 #pragma unroll
   for (int i = 0; i < 16; i++) acc[i] = 0.0;
@@ -120,7 +119,7 @@ __global__ void __launch_bounds__(kReduceBlock) inlier_moments_kernel(const floa
     acc[10] += D1 * S0; acc[11] += D1 * S1; acc[12] += D1 * S2;
     acc[13] += D2 * S0; acc[14] += D2 * S1; acc[15] += D2 * S2;
   }
-  grid_reduce<16>(acc, partials, counter, result);
+  grid_reduce<16>(acc, rs);
 }
 
 __global__ void gather_pairs_kernel(const float* __restrict__ dst, const float* __restrict__ src,
@@ -368,10 +367,10 @@ int cb_ransac_rigid(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, u
   // no hypothesis ever reached sample_size inliers: model_inliers_ is empty, so the re-estimation
   // is a Kabsch over zero pairs = identity (transform_estimation.hpp:20-23)
   if (rc == CB_OK && re_estimate && have_best) {  // :118-128
-    CB_TRY(ensure_scratch(ctx, (size_t)ctx->sm_count * 4 * 16));
     const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 4, (n + kReduceBlock - 1) / kReduceBlock));
-    inlier_moments_kernel<<<blocks, kReduceBlock, 0, ctx->stream>>>(dst->d_raw, src->d_raw, n, rigid_of(best_T), x_max,
-                                                                    ctx->d_partials, ctx->d_counter, ctx->d_result);
+    ReduceScratch rs;
+    CB_TRY(get_reduce_scratch(ctx, blocks, 16, &rs));
+    inlier_moments_kernel<<<blocks, kReduceBlock, 0, ctx->stream>>>(dst->d_raw, src->d_raw, n, rigid_of(best_T), x_max, rs);
     ctx->launches += 1;
     double m[16];
     cudaMemcpyAsync(ctx->h_result, ctx->d_result, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream);

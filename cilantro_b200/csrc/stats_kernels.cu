@@ -13,8 +13,7 @@ namespace {
 
 // result[0] = n, [1..3] = sum (p - c), [4..9] = sum (p - c)(p - c)^T upper triangle (xx xy xz yy yz zz)
 __global__ void __launch_bounds__(kReduceBlock) moments_kernel(const float* __restrict__ raw, size_t n, float cx,
-                                                               float cy, float cz, double* partials,
-                                                               unsigned int* counter, double* result) {
+                                                               float cy, float cz, const ReduceScratch rs) {
   double acc[kMomentValues];
 #pragma unroll
   for (int i = 0; i < kMomentValues; i++) acc[i] = 0.0;
@@ -34,16 +33,16 @@ __global__ void __launch_bounds__(kReduceBlock) moments_kernel(const float* __re
     acc[8] += y * z;
     acc[9] += z * z;
   }
-  grid_reduce<kMomentValues>(acc, partials, counter, result);
+  grid_reduce<kMomentValues>(acc, rs);
 }
 
 }  // namespace
 
 int launch_moments(cb_context* ctx, const float* d_raw, size_t n, const float* shift3) {
   int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 4, (n + kReduceBlock - 1) / kReduceBlock));
-  CB_TRY(ensure_scratch(ctx, (size_t)blocks * kMomentValues));
-  moments_kernel<<<blocks, kReduceBlock, 0, ctx->stream>>>(d_raw, n, shift3[0], shift3[1], shift3[2], ctx->d_partials,
-                                                         ctx->d_counter, ctx->d_result);
+  ReduceScratch rs;
+  CB_TRY(get_reduce_scratch(ctx, blocks, kMomentValues, &rs));
+  moments_kernel<<<blocks, kReduceBlock, 0, ctx->stream>>>(d_raw, n, shift3[0], shift3[1], shift3[2], rs);
   ctx->launches += 1;
   CB_CUDA(cudaGetLastError());
   return CB_OK;

@@ -1,0 +1,629 @@
+// cilantro_b200 — header-only C++ mirror of the cilantro types on the rigid-ICP / k-means / RANSAC /
+// PCA hot path, forwarding to the C ABI of libcilantro_b200.so (include/cilantro_b200.h).
+//
+// Same names, argument meaning and error behaviour as the reference (paths relative to
+// /root/reference/include/cilantro/):
+//   VectorSet3f / ConstVectorSetMatrixMap3f / Vector3f      core/data_containers.hpp:73-156
+//   RigidTransform3f                                        core/space_transformations.hpp:54-57
+//   Neighbor / NeighborSet                                  core/nearest_neighbors.hpp
+//   Correspondence / CorrespondenceSet                      core/correspondence.hpp:9-55
+//   KDTree3f<>                                              core/kd_tree.hpp:144-397
+//   SimplePointToPointMetricRigidICP3f                      registration/icp_common_instances.hpp:250
+//   SimpleCombinedMetricRigidICP3f                          registration/icp_common_instances.hpp:261
+//   KMeans3f<>                                              clustering/kmeans.hpp:9-59,205-207
+//   RigidTransformRANSACEstimator3f<>                       model_estimation/ransac_transform_estimator.hpp:9-122
+//   PrincipalComponentAnalysis3f                            core/principal_component_analysis.hpp:8-89
+//   PointCloud3f (points / normals / colors, size, hasNormals, transform)
+//                                                           utilities/point_cloud.hpp:14-22,557
+//   Timer                                                   utilities/timer.hpp
+// Eigen3 is an external dependency of cilantro that is absent from the build image, so the containers
+// below are minimal Eigen-free stand-ins with the memory layout cilantro uses (column-major 3 x N,
+// packed xyz). A cilantro maintainer keeps Eigen and only swaps the method bodies.
+//
+// Arbitrary user functors (weight / distance evaluators) cannot cross a C ABI: this path implements
+// cilantro's defaults (DistanceEvaluator = identity, UnityWeightEvaluator); anything else is a
+// compile-time error here, never a silent CPU fallback.
+#pragma once
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../cilantro_b200.h"
+
+namespace cilantro {
+
+// ---- containers -----------------------------------------------------------------------------------
+struct Vector3f {
+  float v[3] = {0.f, 0.f, 0.f};
+  Vector3f() = default;
+  Vector3f(float x, float y, float z) : v{x, y, z} {}
+  float& operator[](size_t i) { return v[i]; }
+  float operator[](size_t i) const { return v[i]; }
+  float* data() { return v; }
+  const float* data() const { return v; }
+  float norm() const { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+};
+
+// Owning 3 x N column-major float matrix (cilantro::VectorSet<float,3>).
+class VectorSet3f {
+public:
+  VectorSet3f() = default;
+  VectorSet3f(size_t rows, size_t cols) : d_(3 * cols) { (void)rows; }
+  size_t rows() const { return 3; }
+  size_t cols() const { return d_.size() / 3; }
+  void resize(size_t /*rows*/, size_t cols) { d_.resize(3 * cols); }
+  float* data() { return d_.data(); }
+  const float* data() const { return d_.data(); }
+  float& operator()(size_t r, size_t c) { return d_[3 * c + r]; }
+  float operator()(size_t r, size_t c) const { return d_[3 * c + r]; }
+  Vector3f col(size_t c) const { return Vector3f(d_[3 * c], d_[3 * c + 1], d_[3 * c + 2]); }
+  void setCol(size_t c, const Vector3f& p) {
+    d_[3 * c] = p[0];
+    d_[3 * c + 1] = p[1];
+    d_[3 * c + 2] = p[2];
+  }
+
+private:
+  std::vector<float> d_;
+};
+
+// Non-owning view (cilantro::ConstVectorSetMatrixMap<float,3>): implicit from the same sources as
+// the reference's (VectorSet, std::vector<float>, std::vector<Vector3f>, raw pointer + count).
+class ConstVectorSetMatrixMap3f {
+public:
+  ConstVectorSetMatrixMap3f(const float* data = nullptr, size_t n = 0) : p_(data), n_(n) {}
+  ConstVectorSetMatrixMap3f(const VectorSet3f& s) : p_(s.data()), n_(s.cols()) {}
+  ConstVectorSetMatrixMap3f(const std::vector<float>& s) : p_(s.data()), n_(s.size() / 3) {}
+  ConstVectorSetMatrixMap3f(const std::vector<Vector3f>& s)
+      : p_(s.empty() ? nullptr : s[0].data()), n_(s.size()) {}
+  const float* data() const { return p_; }
+  size_t cols() const { return n_; }
+  size_t rows() const { return 3; }
+  Vector3f col(size_t c) const { return Vector3f(p_[3 * c], p_[3 * c + 1], p_[3 * c + 2]); }
+
+private:
+  const float* p_;
+  size_t n_;
+};
+
+// Rigid transform, row-major [R | t] storage; the accessor surface of Eigen::Transform<float,3,Isometry>
+// that cilantro's examples use.
+class RigidTransform3f {
+public:
+  RigidTransform3f() { setIdentity(); }
+  explicit RigidTransform3f(const float* T12) { std::memcpy(m_, T12, sizeof(m_)); }
+  static RigidTransform3f Identity() { return RigidTransform3f(); }
+  void setIdentity() {
+    for (float& x : m_) x = 0.f;
+    m_[0] = m_[5] = m_[10] = 1.f;
+  }
+  float& linear(size_t r, size_t c) { return m_[4 * r + c]; }
+  float linear(size_t r, size_t c) const { return m_[4 * r + c]; }
+  float& translation(size_t r) { return m_[4 * r + 3]; }
+  float translation(size_t r) const { return m_[4 * r + 3]; }
+  const float* data() const { return m_; }
+  float* data() { return m_; }
+  std::array<float, 16> matrix() const {
+    std::array<float, 16> M{};
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 4; c++) M[4 * r + c] = m_[4 * r + c];
+    M[15] = 1.f;
+    return M;
+  }
+  Vector3f operator*(const Vector3f& p) const {
+    Vector3f q;
+    for (int r = 0; r < 3; r++) q[r] = (m_[4 * r] * p[0] + (m_[4 * r + 1] * p[1] + m_[4 * r + 2] * p[2])) + m_[4 * r + 3];
+    return q;
+  }
+  RigidTransform3f operator*(const RigidTransform3f& o) const {
+    RigidTransform3f r;
+    cb_compose(m_, o.m_, r.m_);
+    return r;
+  }
+  RigidTransform3f inverse() const {
+    RigidTransform3f r;
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) r.m_[4 * i + j] = m_[4 * j + i];
+      r.m_[4 * i + 3] = -(m_[i] * m_[3] + m_[4 + i] * m_[7] + m_[8 + i] * m_[11]);
+    }
+    return r;
+  }
+
+private:
+  float m_[12];
+};
+
+template <typename ScalarT = float, typename IndexT = size_t>
+struct Neighbor {
+  IndexT index;
+  ScalarT value;
+};
+template <typename ScalarT = float, typename IndexT = size_t>
+using NeighborSet = std::vector<Neighbor<ScalarT, IndexT>>;
+template <typename ScalarT = float, typename IndexT = size_t>
+using Neighborhood = NeighborSet<ScalarT, IndexT>;
+
+template <typename ScalarT = float, typename IndexT = size_t>
+struct Correspondence {
+  IndexT indexInFirst;
+  IndexT indexInSecond;
+  ScalarT value;
+};
+template <typename ScalarT = float, typename IndexT = size_t>
+using CorrespondenceSet = std::vector<Correspondence<ScalarT, IndexT>>;
+
+class Timer {  // utilities/timer.hpp:7-43
+public:
+  void start() { t0_ = std::chrono::high_resolution_clock::now(); }
+  void stop() { t1_ = std::chrono::high_resolution_clock::now(); }
+  double getElapsedTime() const { return std::chrono::duration<double, std::milli>(t1_ - t0_).count(); }
+
+private:
+  std::chrono::high_resolution_clock::time_point t0_, t1_;
+};
+
+// ---- library plumbing -------------------------------------------------------------------------------
+namespace b200 {
+
+inline void check(int rc, const char* what) {
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + cb_last_error());
+}
+
+// the reference seeds from std::random_device (kmeans.hpp:41, ransac_base.hpp:73); so does the
+// default here, and setRandomSeed() / the seed argument make runs reproducible
+inline uint32_t random_seed() { return std::random_device{}(); }
+
+// One context per process and device (cb_context is not thread-safe: like the reference's objects,
+// use one thread per set of objects).
+class Context {
+public:
+  static cb_context* get(int device = 0) {
+    static Context c(device);
+    return c.ctx_;
+  }
+
+private:
+  explicit Context(int device) { check(cb_context_create(device, &ctx_), "cb_context_create"); }
+  ~Context() { /* process lifetime; objects holding clouds may outlive static destruction order */ }
+  cb_context* ctx_ = nullptr;
+};
+
+struct CloudHandle {
+  cb_cloud* h = nullptr;
+  CloudHandle() = default;
+  CloudHandle(const ConstVectorSetMatrixMap3f& pts, const ConstVectorSetMatrixMap3f* normals = nullptr) {
+    const float* n = (normals && normals->cols() == pts.cols() && pts.cols() > 0) ? normals->data() : nullptr;
+    check(cb_cloud_create(Context::get(), pts.data(), n, pts.cols(), 0, &h), "cb_cloud_create");
+  }
+  CloudHandle(const CloudHandle&) = delete;
+  CloudHandle& operator=(const CloudHandle&) = delete;
+  ~CloudHandle() {
+    if (h) cb_cloud_destroy(h);
+  }
+};
+
+}  // namespace b200
+
+// ---- KDTree3f<> ------------------------------------------------------------------------------------
+// The "tree" is the device-resident uniform grid; queries are exact (same result set as the kd-tree,
+// ties broken on the lower index).
+template <typename IndexT = size_t>
+class KDTree3f {
+public:
+  using NeighborResult = Neighbor<float, IndexT>;
+  using NeighborhoodResult = NeighborSet<float, IndexT>;
+  using NeighborhoodSetResult = std::vector<NeighborhoodResult>;
+
+  KDTree3f(const ConstVectorSetMatrixMap3f& data, size_t /*max_leaf_size*/ = 10, size_t /*num_build_threads*/ = 1)
+      : n_(data.cols()), cloud_(data) {}
+
+  bool isEmpty() const { return n_ == 0; }
+
+  // single-point queries (core/kd_tree.hpp:181-193, 215-230, 283-299)
+  NeighborResult nearestNeighborSearch(const Vector3f& q) const {
+    NeighborhoodResult r = kNNInRadiusSearch(q, 1, std::numeric_limits<float>::max());
+    if (r.empty()) throw std::runtime_error("nearestNeighborSearch on an empty tree");  // nanoflann.hpp:1715-1718
+    return r[0];
+  }
+  NeighborhoodResult kNNSearch(const Vector3f& q, size_t k) const {
+    return kNNInRadiusSearch(q, k, std::numeric_limits<float>::max());
+  }
+  NeighborhoodResult kNNInRadiusSearch(const Vector3f& q, size_t k, float radius) const {
+    NeighborhoodSetResult r = kNNInRadiusSearch(ConstVectorSetMatrixMap3f(q.data(), 1), k, radius);
+    return r.empty() ? NeighborhoodResult() : r[0];
+  }
+  // batched queries (core/kd_tree.hpp:196-213, 232-249, 301-318)
+  NeighborhoodResult nearestNeighborSearch(const ConstVectorSetMatrixMap3f& queries) const {
+    std::vector<int64_t> idx(queries.cols());
+    std::vector<float> d2(queries.cols());
+    b200::CloudHandle q(queries);
+    b200::check(cb_knn1_radius(b200::Context::get(), cloud_.h, q.h, nullptr, std::numeric_limits<float>::max(),
+                               idx.data(), d2.data()),
+                "cb_knn1_radius");
+    NeighborhoodResult out(queries.cols());
+    for (size_t i = 0; i < out.size(); i++) out[i] = {static_cast<IndexT>(idx[i]), d2[i]};
+    return out;
+  }
+  NeighborhoodSetResult kNNSearch(const ConstVectorSetMatrixMap3f& queries, size_t k) const {
+    return kNNInRadiusSearch(queries, k, std::numeric_limits<float>::max());
+  }
+  NeighborhoodSetResult kNNInRadiusSearch(const ConstVectorSetMatrixMap3f& queries, size_t k, float radius) const {
+    const size_t nq = queries.cols();
+    NeighborhoodSetResult out(nq);
+    if (nq == 0 || k == 0 || n_ == 0) return out;
+    if (k > 32) throw std::runtime_error("cilantro_b200: kNN supports k <= 32");
+    std::vector<int64_t> idx(nq * k);
+    std::vector<float> d2(nq * k);
+    std::vector<uint32_t> cnt(nq);
+    b200::CloudHandle q(queries);
+    b200::check(cb_knn_radius(b200::Context::get(), cloud_.h, q.h, nullptr, (int)k, radius, idx.data(), d2.data(),
+                              cnt.data()),
+                "cb_knn_radius");
+    for (size_t i = 0; i < nq; i++) {
+      out[i].resize(cnt[i]);
+      for (uint32_t j = 0; j < cnt[i]; j++) out[i][j] = {static_cast<IndexT>(idx[i * k + j]), d2[i * k + j]};
+    }
+    return out;
+  }
+
+private:
+  size_t n_;
+  b200::CloudHandle cloud_;
+};
+
+// ---- ICP ---------------------------------------------------------------------------------------------
+enum struct CorrespondenceSearchDirection { FIRST_TO_SECOND, SECOND_TO_FIRST, BOTH };
+
+// The part of CorrespondenceSearchKDTree's fluent surface that the default SECOND_TO_FIRST path uses
+// (correspondence_search/correspondence_search_kd_tree.hpp:237-285).
+class CorrespondenceSearchEngineB200 {
+public:
+  using SearchResult = CorrespondenceSet<float, size_t>;
+  float getMaxDistance() const { return max_distance_; }
+  CorrespondenceSearchEngineB200& setMaxDistance(float dist_thresh_squared) {
+    max_distance_ = dist_thresh_squared;
+    return *this;
+  }
+  const CorrespondenceSearchDirection& getSearchDirection() const { return dir_; }
+  CorrespondenceSearchEngineB200& setSearchDirection(const CorrespondenceSearchDirection& d) {
+    if (d != CorrespondenceSearchDirection::SECOND_TO_FIRST)
+      throw std::runtime_error("cilantro_b200: only SECOND_TO_FIRST correspondence search is implemented");
+    dir_ = d;
+    return *this;
+  }
+  double getInlierFraction() const { return 1.0; }
+  bool getRequireReciprocality() const { return false; }
+  bool getOneToOne() const { return false; }
+  const SearchResult& getCorrespondences() const { return corr_; }
+
+private:
+  template <int>
+  friend class SimpleRigidICP3fB200;
+  float max_distance_ = (float)(0.01 * 0.01);  // correspondence_search_kd_tree.hpp:49
+  CorrespondenceSearchDirection dir_ = CorrespondenceSearchDirection::SECOND_TO_FIRST;
+  SearchResult corr_;
+};
+
+template <int kMetric>
+class SimpleRigidICP3fB200 {
+public:
+  using Transform = RigidTransform3f;
+
+  // point-to-point: (dst, src); combined: (dst, dst_normals, src[, src_normals])
+  SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src)
+      : dst_(dst), src_(src) {
+    init();
+  }
+  SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
+                       const ConstVectorSetMatrixMap3f& src)
+      : dst_(dst, &dst_n), src_(src) {
+    init();
+  }
+  SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
+                       const ConstVectorSetMatrixMap3f& src, const ConstVectorSetMatrixMap3f& src_n)
+      : dst_(dst, &dst_n), src_(src, &src_n) {
+    init();
+  }
+  ~SimpleRigidICP3fB200() {
+    if (icp_) cb_icp_destroy(icp_);
+  }
+  SimpleRigidICP3fB200(const SimpleRigidICP3fB200&) = delete;
+
+  CorrespondenceSearchEngineB200& correspondenceSearchEngine() { return engine_; }
+  const CorrespondenceSearchEngineB200& correspondenceSearchEngine() const { return engine_; }
+
+  // IterativeClosestPointBase surface (registration/icp_base.hpp:40-106)
+  size_t getMaxNumberOfIterations() const { return prm_.max_iter; }
+  SimpleRigidICP3fB200& setMaxNumberOfIterations(size_t n) {
+    prm_.max_iter = (int32_t)n;
+    return *this;
+  }
+  size_t getNumberOfPerformedIterations() const { return res_.iterations; }
+  float getConvergenceTolerance() const { return prm_.tol; }
+  SimpleRigidICP3fB200& setConvergenceTolerance(float tol) {
+    prm_.tol = tol;
+    return *this;
+  }
+  RigidTransform3f getInitialTransform() const { return RigidTransform3f(prm_.T_init); }
+  SimpleRigidICP3fB200& setInitialTransform(const RigidTransform3f& T) {
+    std::memcpy(prm_.T_init, T.data(), sizeof(prm_.T_init));
+    return *this;
+  }
+  float getLastUpdateNorm() const { return res_.last_delta; }
+  bool hasConverged() const { return res_.last_delta < prm_.tol; }
+  const RigidTransform3f& getTransform() const { return T_; }
+
+  // CombinedMetricSingleTransformICP surface (icp_single_transform_combined_metric.hpp:103-141)
+  float getPointToPointMetricWeight() const { return prm_.w_pt; }
+  SimpleRigidICP3fB200& setPointToPointMetricWeight(float w) {
+    prm_.w_pt = w;
+    return *this;
+  }
+  float getPointToPlaneMetricWeight() const { return prm_.w_pl; }
+  SimpleRigidICP3fB200& setPointToPlaneMetricWeight(float w) {
+    prm_.w_pl = w;
+    return *this;
+  }
+  size_t getMaxNumberOfOptimizationStepIterations() const { return prm_.max_opt_iter; }
+  SimpleRigidICP3fB200& setMaxNumberOfOptimizationStepIterations(size_t n) {
+    prm_.max_opt_iter = (int32_t)n;
+    return *this;
+  }
+  float getOptimizationStepConvergenceTolerance() const { return prm_.opt_tol; }
+  SimpleRigidICP3fB200& setOptimizationStepConvergenceTolerance(float tol) {
+    prm_.opt_tol = tol;
+    return *this;
+  }
+
+  SimpleRigidICP3fB200& estimate() {
+    prm_.max_d2 = engine_.max_distance_;
+    b200::check(cb_icp_estimate(icp_, &prm_, &res_), "cb_icp_estimate");
+    T_ = RigidTransform3f(res_.T);
+    corr_fresh_ = false;
+    return *this;
+  }
+  SimpleRigidICP3fB200& estimate(size_t max_iter, float conv_tol) {
+    prm_.max_iter = (int32_t)max_iter;
+    prm_.tol = conv_tol;
+    return estimate();
+  }
+
+  // correspondenceSearchEngine().getCorrespondences() after estimate(): materialised on demand
+  const CorrespondenceSet<float, size_t>& getCorrespondences() {
+    if (!corr_fresh_) {
+      const size_t n = cb_cloud_size(src_.h);
+      std::vector<uint64_t> a(n), b(n);
+      std::vector<float> v(n);
+      size_t cnt = 0;
+      b200::check(cb_icp_correspondences(icp_, a.data(), b.data(), v.data(), &cnt), "cb_icp_correspondences");
+      engine_.corr_.resize(cnt);
+      for (size_t i = 0; i < cnt; i++) engine_.corr_[i] = {(size_t)a[i], (size_t)b[i], v[i]};
+      corr_fresh_ = true;
+    }
+    return engine_.corr_;
+  }
+
+  // getResiduals() -> computeResiduals() (icp_base.hpp:102-104): 1 x N_src
+  std::vector<float> getResiduals() {
+    std::vector<float> r(cb_cloud_size(src_.h));
+    prm_.max_d2 = engine_.max_distance_;
+    b200::check(cb_icp_residuals(icp_, &prm_, T_.data(), r.data()), "cb_icp_residuals");
+    return r;
+  }
+
+  double getLastEstimateDeviceMilliseconds() const { return res_.gpu_ms_total; }
+
+private:
+  void init() {
+    cb_icp_default_params(&prm_);
+    prm_.metric = kMetric;
+    std::memset(&res_, 0, sizeof(res_));
+    res_.last_delta = std::numeric_limits<float>::infinity();
+    b200::check(cb_icp_create(b200::Context::get(), dst_.h, src_.h, &icp_), "cb_icp_create");
+  }
+  b200::CloudHandle dst_, src_;
+  cb_icp* icp_ = nullptr;
+  cb_icp_params prm_;
+  cb_icp_result res_;
+  RigidTransform3f T_;
+  CorrespondenceSearchEngineB200 engine_;
+  bool corr_fresh_ = false;
+};
+
+using SimplePointToPointMetricRigidICP3f = SimpleRigidICP3fB200<CB_ICP_POINT_TO_POINT>;
+using SimpleCombinedMetricRigidICP3f = SimpleRigidICP3fB200<CB_ICP_COMBINED>;
+
+// transformPoints(tform, in, out) — core/space_transformations.hpp:203-216
+inline void transformPoints(const RigidTransform3f& tform, const ConstVectorSetMatrixMap3f& points, VectorSet3f& result) {
+  result.resize(3, points.cols());
+  b200::check(cb_transform_points(b200::Context::get(), tform.data(), points.data(), points.cols(), result.data()),
+              "cb_transform_points");
+}
+
+// ---- KMeans3f<> -------------------------------------------------------------------------------------
+template <typename PointIndexT = size_t, typename ClusterIndexT = size_t>
+class KMeans3f {
+public:
+  using ClusterToPointIndicesMap = std::vector<std::vector<PointIndexT>>;
+  using PointToClusterIndexMap = std::vector<ClusterIndexT>;
+
+  KMeans3f(const ConstVectorSetMatrixMap3f& data) : n_(data.cols()), host_(data), cloud_(data) {}
+
+  KMeans3f& cluster(const ConstVectorSetMatrixMap3f& centroids, size_t max_iter = 100,
+                    float tol = std::numeric_limits<float>::epsilon(), bool use_kd_tree = false) {
+    (void)use_kd_tree;  // both branches of the reference compute the same assignment; one GPU kernel here
+    centroids_.resize(3, centroids.cols());
+    std::memcpy(centroids_.data(), centroids.data(), 3 * centroids.cols() * sizeof(float));
+    return run(max_iter, tol);
+  }
+  KMeans3f& cluster(size_t num_clusters, size_t max_iter = 100, float tol = std::numeric_limits<float>::epsilon(),
+                    bool use_kd_tree = false, uint32_t seed = b200::random_seed()) {
+    (void)use_kd_tree;
+    const size_t k = std::max<size_t>(1, std::min(num_clusters, n_));  // kmeans.hpp:34-36
+    std::vector<uint64_t> idx(k);
+    b200::check(cb_kmeans_seed_indices(n_, k, seed, idx.data()), "cb_kmeans_seed_indices");
+    centroids_.resize(3, k);
+    for (size_t j = 0; j < k; j++) centroids_.setCol(j, host_.col(idx[j]));
+    return run(max_iter, tol);
+  }
+  const VectorSet3f& getClusterCentroids() const { return centroids_; }
+  size_t getNumberOfPerformedIterations() const { return iterations_; }
+  const PointToClusterIndexMap& getPointToClusterIndexMap() const { return labels_; }
+  const ClusterToPointIndicesMap& getClusterToPointIndicesMap() const { return lists_; }
+  size_t getNumberOfClusters() const { return lists_.size(); }
+  size_t getNumberOfPoints() const { return labels_.size(); }
+
+private:
+  struct std_seed_helper {};
+  KMeans3f& run(size_t max_iter, float tol) {
+    std::vector<uint64_t> lab(n_);
+    cb_kmeans_result r;
+    b200::check(cb_kmeans_cluster(b200::Context::get(), cloud_.h, centroids_.data(), centroids_.cols(), max_iter, tol,
+                                  lab.data(), &r),
+                "cb_kmeans_cluster");
+    iterations_ = r.iterations;
+    labels_.assign(lab.begin(), lab.end());
+    lists_.assign(centroids_.cols(), {});  // clustering_base.hpp:22-32
+    for (size_t i = 0; i < labels_.size(); i++)
+      if ((size_t)labels_[i] < lists_.size()) lists_[labels_[i]].emplace_back((PointIndexT)i);
+    return *this;
+  }
+  size_t n_;
+  ConstVectorSetMatrixMap3f host_;
+  b200::CloudHandle cloud_;
+  VectorSet3f centroids_;
+  size_t iterations_ = 0;
+  PointToClusterIndexMap labels_;
+  ClusterToPointIndicesMap lists_;
+};
+
+// ---- RigidTransformRANSACEstimator3f<> ----------------------------------------------------------------
+template <typename IndexT = size_t>
+class RigidTransformRANSACEstimator3f {
+public:
+  using Model = RigidTransform3f;
+  using ResidualVector = std::vector<float>;
+  using IndexVector = std::vector<IndexT>;
+
+  RigidTransformRANSACEstimator3f(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src)
+      : n_(dst.cols()), dst_(dst), src_(src) {
+    defaults();
+  }
+  template <class CorrespondencesT>
+  RigidTransformRANSACEstimator3f(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src,
+                                  const CorrespondencesT& corr)
+      : n_(corr.size()), dst_g_(gather(dst, corr, true)), src_g_(gather(src, corr, false)), dst_(dst_g_), src_(src_g_) {
+    defaults();
+  }
+
+  // RandomSampleConsensusBase setters (model_estimation/ransac_base.hpp:29-62)
+  RigidTransformRANSACEstimator3f& setMaxInlierResidual(float t) { thresh_ = t; return *this; }
+  RigidTransformRANSACEstimator3f& setTargetInlierCount(size_t c) { target_ = c; return *this; }
+  RigidTransformRANSACEstimator3f& setMaxNumberOfIterations(size_t n) { max_iter_ = n; return *this; }
+  RigidTransformRANSACEstimator3f& setReEstimationStep(bool b) { re_estimate_ = b; return *this; }
+  RigidTransformRANSACEstimator3f& setRandomSeed(uint32_t s) { seed_ = s; return *this; }  // injected
+  float getMaxInlierResidual() const { return thresh_; }
+  size_t getTargetInlierCount() const { return target_; }
+  size_t getMaxNumberOfIterations() const { return max_iter_; }
+  bool getReEstimationStep() const { return re_estimate_; }
+
+  RigidTransformRANSACEstimator3f& estimate() {
+    cb_ransac_result r;
+    std::vector<uint64_t> inl(n_);
+    residuals_.resize(n_);
+    b200::check(cb_ransac_rigid(b200::Context::get(), dst_.h, src_.h, seed_, target_, max_iter_, thresh_,
+                                re_estimate_ ? 1 : 0, &r, inl.data(), residuals_.data()),
+                "cb_ransac_rigid");
+    model_ = RigidTransform3f(r.T);
+    iterations_ = r.iterations;
+    inliers_.assign(inl.begin(), inl.begin() + r.num_inliers);
+    return *this;
+  }
+  RigidTransformRANSACEstimator3f& estimate(float max_residual, size_t target_inlier_count, size_t max_iter) {
+    thresh_ = max_residual;
+    target_ = target_inlier_count;
+    max_iter_ = max_iter;
+    return estimate();
+  }
+  const Model& getModel() const { return model_; }
+  const ResidualVector& getModelResiduals() const { return residuals_; }
+  const IndexVector& getModelInliers() const { return inliers_; }
+  bool targetInlierCountAchieved() const { return inliers_.size() >= target_; }
+  size_t getNumberOfPerformedIterations() const { return iterations_; }
+  size_t getNumberOfInliers() const { return inliers_.size(); }
+
+private:
+  void defaults() {  // ransac_transform_estimator.hpp:27
+    target_ = n_ / 2 + n_ % 2;
+    max_iter_ = 100;
+    thresh_ = 0.01f;
+    re_estimate_ = true;
+    seed_ = b200::random_seed();
+  }
+  template <class CorrespondencesT>
+  static VectorSet3f gather(const ConstVectorSetMatrixMap3f& pts, const CorrespondencesT& corr, bool first) {
+    VectorSet3f out(3, corr.size());  // :31-44
+    for (size_t i = 0; i < corr.size(); i++) out.setCol(i, pts.col(first ? corr[i].indexInFirst : corr[i].indexInSecond));
+    return out;
+  }
+  size_t n_;
+  VectorSet3f dst_g_, src_g_;
+  b200::CloudHandle dst_, src_;
+  size_t target_, max_iter_, iterations_ = 0;
+  float thresh_;
+  bool re_estimate_;
+  uint32_t seed_;
+  Model model_;
+  ResidualVector residuals_;
+  IndexVector inliers_;
+};
+
+// ---- PrincipalComponentAnalysis3f -----------------------------------------------------------------------
+class PrincipalComponentAnalysis3f {
+public:
+  PrincipalComponentAnalysis3f(const ConstVectorSetMatrixMap3f& data, bool /*parallel*/ = false) {
+    b200::CloudHandle c(data);
+    b200::check(cb_pca(b200::Context::get(), c.h, mean_.data(), cov_.data(), evals_.data(), evecs_.data()), "cb_pca");
+  }
+  const Vector3f& getDataMean() const { return mean_; }
+  const std::array<float, 9>& getDataCovariance() const { return cov_; }  // row-major 3x3
+  const Vector3f& getEigenValues() const { return evals_; }               // descending
+  const std::array<float, 9>& getEigenVectors() const { return evecs_; }  // row-major, columns = eigenvectors
+
+private:
+  Vector3f mean_, evals_;
+  std::array<float, 9> cov_{}, evecs_{};
+};
+
+// ---- PointCloud3f ------------------------------------------------------------------------------------------
+struct PointCloud3f {
+  VectorSet3f points, normals, colors;
+  size_t size() const { return points.cols(); }
+  bool hasNormals() const { return size() > 0 && normals.cols() == size(); }
+  bool hasColors() const { return size() > 0 && colors.cols() == size(); }
+  bool isEmpty() const { return size() == 0; }
+  PointCloud3f& transform(const RigidTransform3f& T) {  // utilities/point_cloud.hpp (rigid overload)
+    VectorSet3f out;
+    transformPoints(T, points, out);
+    points = out;
+    if (hasNormals()) {
+      RigidTransform3f R = T;
+      for (int r = 0; r < 3; r++) R.translation(r) = 0.f;
+      transformPoints(R, normals, out);
+      normals = out;
+    }
+    return *this;
+  }
+};
+
+}  // namespace cilantro

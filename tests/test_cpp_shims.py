@@ -1,0 +1,33 @@
+"""The C++ drop-in surface (include/cilantro/*.hpp over the C ABI): compiles without Eigen on CPU;
+on the GPU box the reference-example calls in tests/cpp/test_shims.cpp run end to end."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_shims.cpp")
+INC = os.path.join(ROOT, "include")
+LIBDIR = os.path.join(ROOT, "cilantro_b200")
+
+
+def _env():
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    return env
+
+
+def test_shim_headers_compile_without_eigen():
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", INC, SRC], env=_env())
+
+
+@pytest.mark.gpu
+def test_reference_examples_through_cpp_shims(cb, tmp_path):
+    exe = str(tmp_path / "test_shims")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", INC, SRC, "-o", exe, "-L", LIBDIR, "-lcilantro_b200",
+                           f"-Wl,-rpath,{LIBDIR}"], env=_env())
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "all C++ shim checks passed" in out.stdout
