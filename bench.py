@@ -238,11 +238,12 @@ def run_ours(args, w):
     barrier(world)
     wall = time.perf_counter() - t0
     launches = ctx.kernel_launches() - launches0
-    # keep the GPU busy a little longer for the clock sampler on very short runs
+    # keep the GPUs busy a little longer for the clock sampler on very short runs; EVERY rank runs
+    # it (the iteration contains a collective), the decision is taken on the max-over-ranks wall time
     clocks = None
+    if cdist.max_over_ranks(wall) < 0.5:
+        icp.estimate(max_iter=max(args.steps, 50), flush_l2=False, **kw)
     if rank == 0:
-        if wall < 0.5:
-            icp.estimate(max_iter=max(args.steps, 50), flush_l2=False, **kw)
         clocks = sampler.stop()
     assert res["iterations"] == args.steps
     ms_total = cdist.max_over_ranks(res["gpu_ms_total"])
@@ -279,10 +280,10 @@ def run_ours(args, w):
         return 0
     # ---- roofline of the dominant kernel (fused transform + grid 1-NN + moment accumulation) -------
     peak, peak_src = load_peaks()
-    # algorithmic bytes per launch: 16 B query read + 8 B (nn_pos, nn_d2) written per source
-    # point, every cell-sorted reference point read once (16 B), + one 16 B normal gather per
-    # correspondence for the plane term
-    algo_bytes = 24 * n_src + 16 * n_dst + (16 * n_src if w["metric"] == "combined" else 0)
+    # algorithmic bytes per launch: 16 B query read per source point, every cell-sorted
+    # reference point read once (16 B), + one 16 B normal gather per correspondence for the plane term
+    # (per-query results are no longer written in the iteration loop)
+    algo_bytes = 16 * n_src + 16 * n_dst + (16 * n_src if w["metric"] == "combined" else 0)
     kernel_ms = ms_kernel / args.steps
     achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -336,10 +337,16 @@ def main():
     ap.add_argument("--steps", type=int, default=15)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="icp_p2p_1m", choices=sorted(WORKLOADS))
+    from bench_aux import AUX
+
+    ap.add_argument("--workload", default="icp_p2p_1m", choices=sorted(WORKLOADS) + sorted(AUX))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload in AUX:  # secondary single-GPU workloads (k-means, RANSAC, PCA): bench_aux.py
+        if int(os.environ.get("RANK", "0")) == 0:
+            AUX[args.workload](args)
+        return 0
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)

@@ -1,0 +1,167 @@
+"""Secondary workloads of bench.py (BASELINE.json configs 4 and 5, and PCA): single GPU, one JSON line each.
+
+    python bench.py --workload kmeans_50m   [--steps K --warmup W]     step = one Lloyd iteration
+    python bench.py --workload ransac_5m    [--steps K --warmup W]     step = one batch of 1000 hypotheses
+    python bench.py --workload pca_50m      [--steps K --warmup W]     step = one mean+covariance pass
+
+Same timing hygiene as the ICP workload (CUDA events inside the library, inputs larger than L2 or an L2
+flush, CPU baseline = the oracle on a bounded sample of the same workload).
+"""
+import json
+import time
+
+import numpy as np
+
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal FMA rate of the FP32 pipe (SMs x lanes x 2 x max clock)
+
+
+def _ctx():
+    import torch
+
+    from cilantro_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench needs a CUDA device: cilantro_b200 has no CPU fallback")
+    return capi, capi.Context(0)
+
+
+def kmeans(args, n=50_000_000, k=1024):
+    import oracle
+    from cilantro_b200 import synth
+
+    capi, ctx = _ctx()
+    pts, cent0 = synth.kmeans_data(n, k, seed=1)
+    cloud = capi.Cloud(ctx, pts)
+    # warm-up
+    capi.kmeans_cluster(ctx, cloud, cent0, max_iter=max(args.warmup, 1), tol=0.0, want_labels=False)
+    l0 = ctx.kernel_launches()
+    res = capi.kmeans_cluster(ctx, cloud, cent0, max_iter=args.steps, tol=0.0, want_labels=False)
+    launches = ctx.kernel_launches() - l0
+    ms = res["gpu_ms_total"] / res["iterations"]
+    flop = 8.0 * n * k
+    # e2e: host points -> upload -> cluster(steps) -> centroids + labels on host
+    t0 = time.perf_counter()
+    c2 = capi.Cloud(ctx, pts)
+    r2 = capi.kmeans_cluster(ctx, c2, cent0, max_iter=args.steps, tol=0.0, want_labels=True)
+    e2e_s = time.perf_counter() - t0
+    # CPU baseline: oracle brute-force assignment (OpenMP) + serial update on a bounded sample
+    sample = min(n, 5_000_000)
+    t0 = time.perf_counter()
+    oracle.kmeans(pts[:sample], cent0, max_iter=1, tol=0.0)
+    cpu_s = time.perf_counter() - t0
+    line = {
+        "metric": "kmeans_point_assignments_per_sec", "value": n * 1e3 / ms, "unit": "points/s",
+        "iterations_per_sec": 1e3 / ms, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"KMeans3f: {n} uniform points, K={k}, fixed initial centroids, {args.steps} Lloyd iterations (tol=0)",
+                   "l2": "inputs (600 MB) larger than L2"},
+        "e2e": {"value": n * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": pts.nbytes / args.steps,
+                "d2h_bytes_per_step": (8 * n + 12 * k) / args.steps,
+                "what": f"cb_cloud_create + cb_kmeans_cluster({args.steps}) + labels/centroids on host: {e2e_s:.3f} s"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp32", "achieved": flop / (ms * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": flop / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "traffic": None,
+                     "kernel": "kmeans_assign_kernel", "note": "8 N K flop per iteration (3 sub, 3 mul, 2 add; the "
+                     "arithmetic contract forbids FMA, so the attainable rate is half the FMA peak)"},
+        "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": f"1 Lloyd iteration on the first {sample} points (brute-force assignment, OpenMP; serial update)"},
+    }
+    print(json.dumps(line))
+
+
+def ransac(args, n=5_000_000, batch=1000):
+    import oracle
+    from cilantro_b200 import synth
+
+    capi, ctx = _ctx()
+    dst, src, T_ref, inl = synth.ransac_pairs(n, 0.3, seed=1)
+    d_dst, d_src = capi.Cloud(ctx, dst), capi.Cloud(ctx, src)
+    samples = oracle.ransac_samples(n, 3, batch, seed=7)
+    T_h = oracle.ransac_fit_samples(dst, src, samples)
+    for _ in range(max(args.warmup, 1)):
+        capi.ransac_score(ctx, d_dst, d_src, T_h[:64], 0.01)
+    l0 = ctx.kernel_launches()
+    times = []
+    for _ in range(args.steps):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        counts = capi.ransac_score(ctx, d_dst, d_src, T_h, 0.01)
+        times.append(time.perf_counter() - t0)
+    launches = ctx.kernel_launches() - l0
+    ms = 1e3 * float(np.median(times))
+    flop = 30.0 * n * batch
+    # full loop, 10k hypotheses, early exit disabled (BASELINE config 5)
+    t0 = time.perf_counter()
+    full = capi.ransac_rigid(ctx, d_dst, d_src, seed=11, max_iter=10000, thresh=0.01, inlier_count_thresh=n,
+                             re_estimate=True)
+    full_s = time.perf_counter() - t0
+    err = synth.frobenius(full["T"], T_ref)
+    hyp_cpu = 8
+    t0 = time.perf_counter()
+    oc = oracle.ransac_score(dst, src, T_h[:hyp_cpu], 0.01)
+    cpu_s = time.perf_counter() - t0
+    assert np.array_equal(oc, counts[:hyp_cpu]), "GPU inlier counts differ from the oracle"
+    line = {
+        "metric": "ransac_hypotheses_per_sec", "value": batch * 1e3 / ms, "unit": "hypotheses/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RigidTransformRANSACEstimator3f scoring: {n} correspondences (30 % inliers), {batch} hypotheses per step, thresh 0.01",
+                   "l2": "inputs (120 MB) comparable to L2; the pairs are read once per batch"},
+        "e2e": {"value": full["iterations"] / full_s, "unit": "hypotheses/s", "h2d_bytes_per_step": 48.0 * 1000, "d2h_bytes_per_step": 4.0 * 1000,
+                "what": f"cb_ransac_rigid: 10000 hypotheses (sample on host, Kabsch-of-3 on host, batches of 1024 scored on the "
+                        f"device, re-estimation) in {full_s:.3f} s; |T - T_ref|_F = {err:.2e}; inliers {full['num_inliers']}"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "fp32", "achieved": flop / (ms * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": flop / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "traffic": None, "kernel": "ransac_score_kernel",
+                     "note": "~30 flop per pair-hypothesis (SURVEY 8d), no FMA by contract; wall-clock per call incl. 48 KB H2D + 4 KB D2H"},
+        "cpu_baseline": {"value": hyp_cpu / cpu_s, "unit": "hypotheses/s", "cores": oracle.num_threads(), "kind": "port",
+                         "sample": f"{hyp_cpu} hypotheses scored over all {n} pairs (OpenMP over hypotheses)"},
+    }
+    print(json.dumps(line))
+
+
+def pca(args, n=50_000_000):
+    import oracle
+    from cilantro_b200 import synth
+
+    capi, ctx = _ctx()
+    pts, _ = synth.kmeans_data(n, 1, seed=2)
+    cloud = capi.Cloud(ctx, pts)
+    for _ in range(max(args.warmup, 1)):
+        capi.pca(ctx, cloud)
+    times = []
+    l0 = ctx.kernel_launches()
+    for _ in range(args.steps):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        r = capi.pca(ctx, cloud)
+        times.append(time.perf_counter() - t0)
+    launches = ctx.kernel_launches() - l0
+    ms = 1e3 * float(np.median(times))
+    from bench import load_peaks
+
+    peak, src = load_peaks()
+    sample = 10_000_000
+    t0 = time.perf_counter()
+    o = oracle.pca(pts[:sample])
+    cpu_s = time.perf_counter() - t0
+    line = {
+        "metric": "pca_points_per_sec", "value": n * 1e3 / ms, "unit": "points/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 accumulation of f32 points", "data": "synthetic",
+        "config": {"workload": f"PrincipalComponentAnalysis3f: {n} uniform points (mean + covariance + 3x3 eigen)",
+                   "l2": "inputs (600 MB) larger than L2"},
+        "e2e": {"value": None, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 80,
+                "what": "wall clock per cb_pca call on a resident cloud (pivot launch + streaming pass + host eigen-solve)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": 12.0 * n / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": 12.0 * n / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "moments_kernel", "peak_source": src},
+        "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": 1, "kind": "port",
+                         "sample": f"serial two-pass covariance (the reference's default, covariance.hpp:64-76) on {sample} points"},
+    }
+    print(json.dumps(line))
+
+
+AUX = {"kmeans_50m": kmeans, "ransac_5m": ransac, "pca_50m": pca,
+       "kmeans_5m": lambda a: kmeans(a, n=5_000_000, k=256), "ransac_500k": lambda a: ransac(a, n=500_000, batch=256),
+       "pca_5m": lambda a: pca(a, n=5_000_000)}

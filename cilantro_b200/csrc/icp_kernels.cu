@@ -32,7 +32,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) 
 }
 
 #ifndef CB_ICP_MIN_BLOCKS
-#define CB_ICP_MIN_BLOCKS 4
+#define CB_ICP_MIN_BLOCKS 5
 #endif
 
 template <int MODE, bool SEARCH>
@@ -46,6 +46,8 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
   // a low register count. Blocks own 256 consecutive queries of the cell-sorted source cloud, i.e. a
   // compact spatial neighbourhood (L1 reuse of the reference cells).
   __shared__ WarpSearchSmem wsm[SEARCH ? kBlock / 32 : 1];
+  __shared__ AsyncReduceSmem<NV> rsm;
+  if constexpr (MODE != kModeKnn) async_reduce_init(rsm);
   if (SEARCH && threadIdx.x == 0 && a.dst.n > 0) {
     // Software prefetch of the reference arrays into L2, a fixed number of blocks ahead of the
     // consumer front. Both clouds are cell-sorted x-major in (nearly) the same frame, so block b of
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
       }
     }
   }
-  if (MODE != kModeKnn) grid_reduce<NV>(acc, a.rs);
+  if constexpr (MODE != kModeKnn) grid_reduce_async<NV>(acc, a.rs, rsm);
 }
 
 __global__ void __launch_bounds__(kBlock) residual_kernel(const GridView dst, const float4* __restrict__ src_pts,

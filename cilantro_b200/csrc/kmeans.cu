@@ -132,10 +132,18 @@ int kmeans_step(cb_context* ctx, const cb_cloud* pts, const KMeansBuffers& b, co
   const size_t smem_sums = K * 4 * sizeof(double);
   const bool use_smem = smem_sums + kChunk * sizeof(float4) <= 200 * 1024;
   const size_t smem = kChunk * sizeof(float4) + (use_smem ? smem_sums : 0);
-  int per_sm = 2;
-  int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (pts->n + tile - 1) / tile));
+  // persistent grid = SMs x resident blocks per SM (occupancy API with this launch's dynamic smem);
+  // ncu showed 22 % occupancy and 0.74 issue utilisation with a fixed 2 blocks/SM
+  int per_sm = 0;
   if (use_smem) {
     CB_CUDA(cudaFuncSetAttribute(kmeans_assign_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_assign_kernel<true>, kBlock, smem));
+  } else {
+    CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmeans_assign_kernel<false>, kBlock, smem));
+  }
+  per_sm = std::max(1, std::min(per_sm, 6));
+  int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (pts->n + tile - 1) / tile));
+  if (use_smem) {
     kmeans_assign_kernel<true><<<blocks, kBlock, smem, ctx->stream>>>(pts->d_raw, pts->n, b.d_cent, (int)K, b.d_labels,
                                                                      b.d_sums, b.d_changed);
   } else {

@@ -173,7 +173,10 @@ int score_batch(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, const
   const size_t smem = (size_t)kHypChunk * 12 * sizeof(float) + (size_t)H * sizeof(uint32_t);
   CB_CUDA(cudaFuncSetAttribute(ransac_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t tile = (size_t)kBlock * kPairs;
-  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 2, (dst->n + tile - 1) / tile));
+  int per_sm = 0;  // resident blocks per SM for this launch's dynamic shared memory (was a fixed 2: 22 % occupancy)
+  CB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ransac_score_kernel, kBlock, smem));
+  per_sm = std::max(1, std::min(per_sm, 6));
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * per_sm, (dst->n + tile - 1) / tile));
   ransac_score_kernel<<<blocks, kBlock, smem, ctx->stream>>>(dst->d_raw, src->d_raw, dst->n, d_T, H, x_max, d_counts);
   ctx->launches += 1;
   CB_CUDA(cudaGetLastError());

@@ -73,4 +73,119 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NV], const ReduceScrat
   if (threadIdx.x == 0) rs.counters[0] = 0;
 }
 
+// ---- barrier-free variant -----------------------------------------------------------------------
+// Same result and the same fixed summation order, but no warp ever WAITS for another: each warp
+// parks its 32-lane sum in its own shared slot and takes a ticket; the warp that arrives last folds
+// the block's slots, writes the block row and carries on alone through the group / grid levels.
+// Used by the ICP search kernel, whose warps finish at very different times (ncu: a third of the
+// warp residency was spent at the __syncthreads of the barrier version).
+template <int NV>
+struct AsyncReduceSmem {
+  double slot[kReduceBlock / 32][NV];
+  unsigned int arrived;
+};
+
+// Call once at kernel start (all threads), before any warp can reach grid_reduce_async.
+template <int NV>
+__device__ __forceinline__ void async_reduce_init(AsyncReduceSmem<NV>& sm) {
+  if (threadIdx.x == 0) sm.arrived = 0u;
+  __syncthreads();
+}
+
+// one warp sums rows r0..r1-1 of a [rows][NV] table (lane i owns value i; NV <= 32), 8 loads in flight
+template <int NV>
+__device__ __forceinline__ void warp_sum_rows(const double* __restrict__ table, unsigned int r0, unsigned int r1,
+                                              double* __restrict__ out, int lane) {
+  if (lane < NV) {
+    double s = 0;
+    unsigned int b = r0;
+    for (; b + 8 <= r1; b += 8) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) t[u] = __ldcg(table + (size_t)(b + u) * NV + lane);
+#pragma unroll
+      for (int u = 0; u < 8; u++) s += t[u];
+    }
+    for (; b < r1; ++b) s += __ldcg(table + (size_t)b * NV + lane);
+    out[lane] = s;
+  }
+}
+
+// Sum NP (16 or 32) per-lane values over the 32 lanes of a warp with a transposing butterfly:
+// at each step a lane keeps one half of its values and hands the other half to its partner, so the
+// warp spends NP - 1 (+1) shuffles instead of 5 NP. On return v[0] of lane L holds the warp total of
+// value L >> 1 (NP = 16, both lanes of a pair hold it) or of value L (NP = 32). Fixed tree order.
+template <int NP>
+__device__ __forceinline__ double warp_transpose_reduce(double (&v)[NP], int lane) {
+  static_assert(NP == 16 || NP == 32, "NP must be 16 or 32");
+  int off = 16;
+#pragma unroll
+  for (int half = NP / 2; half >= 1; half >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < half; j++) {
+      const double send = up ? v[j] : v[j + half];
+      const double keep = up ? v[j + half] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+    off >>= 1;
+  }
+  if (NP == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+  return v[0];
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const ReduceScratch& rs, AsyncReduceSmem<NV>& sm) {
+  static_assert(NV <= 32, "one lane per value");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kWarps = kReduceBlock / 32;
+  if constexpr (NV == 16) {
+    const double tot = warp_transpose_reduce<16>(acc, lane);
+    if ((lane & 1) == 0) sm.slot[warp][lane >> 1] = tot;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) sm.slot[warp][i] = v;
+    }
+  }
+  __syncwarp();
+  unsigned int t = 0;
+  if (lane == 0) {
+    __threadfence_block();
+    t = atomicAdd(&sm.arrived, 1u);
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != kWarps - 1) return;
+  __threadfence_block();
+  // last warp of the block: block row
+  if (lane < NV) {
+    double s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) s += ((volatile double*)sm.slot[w])[lane];
+    rs.partials[(size_t)blockIdx.x * NV + lane] = s;
+  }
+  const unsigned int ngroups = (gridDim.x + kReduceGroup - 1) / kReduceGroup;
+  const unsigned int g = blockIdx.x / kReduceGroup;
+  const unsigned int g0 = g * kReduceGroup, g1 = min(gridDim.x, g0 + kReduceGroup);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) t = atomicAdd(rs.counters + 1 + g, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != (g1 - g0) - 1) return;
+  __threadfence();
+  warp_sum_rows<NV>(rs.partials, g0, g1, rs.gpartials + (size_t)g * NV, lane);
+  if (lane == 0) rs.counters[1 + g] = 0;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) t = atomicAdd(rs.counters, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != ngroups - 1) return;
+  __threadfence();
+  warp_sum_rows<NV>(rs.gpartials, 0, ngroups, rs.result, lane);
+  if (lane == 0) rs.counters[0] = 0;
+}
+
 }  // namespace cb

@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Turn the ncu captures brought back in gpurun_out/ into the committed summaries of this directory.
+
+    python profiles/summarize.py r01        # reads gpurun_out/prof_r01*.ncu-rep, gpurun_out/launches_r01.csv
+
+Writes profiles/<round>_<kernel>.md (key metrics + top stall reasons + opcode mix of one launch),
+profiles/launches_<round>.csv (copied) + a launch-share table, and profiles/traffic.json (DRAM bytes per
+launch of the dominant kernel, read by bench.py for roofline.traffic).
+"""
+import collections
+import csv
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__grid_size",
+    "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_static",
+    "launch__shared_mem_per_block_dynamic", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
+    "smsp__inst_executed.sum", "sass__thread_inst_executed_per_opcode_category",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "TPC.TriageCompute.sm__cycles_active.avg", "sm__cycles_elapsed.max",
+]
+UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+
+
+def ncu_csv(rep, page, extra=()):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv", *extra], capture_output=True, text=True).stdout
+    return list(csv.reader(out.splitlines()))
+
+
+def summarize(rep, title, note):
+    raw = ncu_csv(rep, "raw")
+    hdr, units, row = raw[0], raw[1], raw[-1]
+    col = {h: i for i, h in enumerate(hdr)}
+    lines = [f"# {title}", "", note, "", f"Capture: `{os.path.basename(rep)}` (ncu --set full --clock-control none --import-source on, one launch).",
+             "Numbers under the profiler are NOT bench values.", "", "| metric | value | unit |", "|---|---:|---|"]
+    for k in KEYS:
+        if k in col and row[col[k]] != "":
+            lines.append(f"| `{k}` | {row[col[k]]} | {units[col[k]]} |")
+    stalls = []
+    for h, i in col.items():
+        if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
+            try:
+                stalls.append((float(row[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")))
+            except ValueError:
+                pass
+    stalls.sort(reverse=True)
+    lines += ["", "Top warp-stall reasons (warps per issue-active cycle):", "", "| stall | ratio |", "|---|---:|"]
+    lines += [f"| {n} | {v:.2f} |" for v, n in stalls[:8]]
+    # opcode mix
+    src = ncu_csv(rep, "source")
+    hi = [i for i, r in enumerate(src) if "Instructions Executed" in r]
+    if hi:
+        h = src[hi[0]]
+        ci, si, ti = h.index("Instructions Executed"), h.index("Source"), h.index("Thread Instructions Executed")
+        agg = collections.defaultdict(lambda: [0, 0])
+        tot = 0
+        for r in src[hi[0] + 1:]:
+            try:
+                n, t = int(r[ci]), int(r[ti])
+            except (ValueError, IndexError):
+                continue
+            m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", r[si].strip())
+            op = m.group(2).split(".")[0] if m else "?"
+            agg[op][0] += n
+            agg[op][1] += t
+            tot += n
+        lines += ["", f"Executed warp-instructions by opcode (total {tot}):", "", "| opcode | warp-instr | share | active threads / instr |",
+                  "|---|---:|---:|---:|"]
+        for op, v in sorted(agg.items(), key=lambda x: -x[1][0])[:14]:
+            lines.append(f"| {op} | {v[0]} | {100 * v[0] / max(tot, 1):.1f}% | {v[1] / max(v[0], 1):.1f} |")
+    traffic = None
+    if "dram__bytes_read.sum" in col:
+        traffic = float(row[col["dram__bytes_read.sum"]]) * UNIT.get(units[col["dram__bytes_read.sum"]], 1.0) + \
+            float(row[col["dram__bytes_write.sum"]]) * UNIT.get(units[col["dram__bytes_write.sum"]], 1.0)
+        lines += ["", f"DRAM traffic of this launch: {traffic / 1e6:.1f} MB."]
+    return "\n".join(lines) + "\n", traffic
+
+
+def launches(csv_path):
+    rows = [l for l in open(csv_path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in csv.DictReader(rows):
+        k = r["Kernel Name"].split("(")[0][-70:]
+        agg[k][0] += 1
+        agg[k][1] += float(r["Metric Value"].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    out = ["| launches | total us | share | avg us | kernel |", "|---:|---:|---:|---:|---|"]
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
+        out.append(f"| {v[0]} | {v[1] / 1e3:.1f} | {100 * v[1] / tot:.1f}% | {v[1] / v[0] / 1e3:.1f} | `{k}` |")
+    return "\n".join(out)
+
+
+def main():
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    jobs = [
+        (f"prof_{rnd}f.ncu-rep", f"{rnd}_icp_pass_kernel.md", "icp_pass_kernel<p2p, search> — bench.py icp_p2p_1m",
+         "1 M -> 1 M point-to-point ICP iteration (fused transform + warp-pooled grid 1-NN + Kabsch moments), L2 flushed before the launch.",
+         "icp_p2p_1m"),
+        (f"prof_{rnd}_kmeans.ncu-rep", f"{rnd}_kmeans_assign_kernel.md", "kmeans_assign_kernel — bench.py kmeans_5m",
+         "5 M points x 256 centroids, fused assignment + per-cluster double sums (shared-memory atomics).", None),
+        (f"prof_{rnd}_ransac.ncu-rep", f"{rnd}_ransac_score_kernel.md", "ransac_score_kernel — bench.py ransac_500k",
+         "500 k correspondences x 256 hypotheses per launch, inlier counts only.", None),
+        (f"prof_{rnd}_moments.ncu-rep", f"{rnd}_moments_kernel.md", "moments_kernel — bench.py pca_50m",
+         "50 M points, one streaming pass (mean + covariance moments in double).", None),
+    ]
+    traffic = {}
+    tpath = os.path.join(HERE, "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    for rep, md, title, note, key in jobs:
+        p = os.path.join(OUT, rep)
+        if not os.path.exists(p):
+            continue
+        text, tr = summarize(p, title, note)
+        open(os.path.join(HERE, md), "w").write(text)
+        if key and tr:
+            traffic[key] = tr
+            traffic["source"] = f"profiles/{md}"
+        print("wrote", md)
+    json.dump(traffic, open(tpath, "w"), indent=1)
+    lp = os.path.join(OUT, f"launches_{rnd}.csv")
+    if os.path.exists(lp):
+        shutil.copy(lp, os.path.join(HERE, f"launches_{rnd}.csv"))
+        open(os.path.join(HERE, f"launches_{rnd}.md"), "w").write(
+            f"# Launch list of one `bench.py --steps 5 --warmup 3` run ({rnd})\n\n`ncu --metrics gpu__time_duration.sum "
+            "--clock-control none` — cold-cache, serialised: compare SHARES, not absolutes. The run contains the value leg\n"
+            "(8 ICP iterations), three end-to-end calls (45 iterations + 6 grid builds) and the initial grid builds.\n\n"
+            + launches(lp) + "\n")
+        print("wrote launches")
+
+
+if __name__ == "__main__":
+    main()
