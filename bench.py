@@ -197,7 +197,8 @@ def workload_config(args, w, world, n_src_rank, n_dst):
                      f"GPU(s) against {n_dst} destination points (uniform random in the unit cube, seed 1, "
                      f"noise +-0.001), max_distance^2={w['max_d2']:g}, fixed iteration count (tol=0)"),
         "parallelism": f"src sharded x{world}, dst replicated, one 16-value (p2p) / 28-value NCCL all-reduce per iteration",
-        "l2": "flushed before every timed iteration (256 MiB memset outside the CUDA-event bracket)",
+        "l2": ("NOT flushed (--no-flush experiment; inputs smaller than L2 stay resident)" if getattr(args, "no_flush", False)
+               else "flushed before every timed iteration (256 MiB memset outside the CUDA-event bracket)"),
     }
 
 
@@ -225,7 +226,7 @@ def run_ours(args, w):
     d_src.grid_info()
     icp = capi.Icp(ctx, d_dst, d_src)
     if args.warmup > 0:
-        icp.estimate(max_iter=args.warmup, flush_l2=True, **kw)
+        icp.estimate(max_iter=args.warmup, flush_l2=not args.no_flush, **kw)
     barrier(world)
     ctx.synchronize()
     sampler = ClockSampler(local)
@@ -233,7 +234,7 @@ def run_ours(args, w):
         sampler.start()
     launches0 = ctx.kernel_launches()
     t0 = time.perf_counter()
-    res = icp.estimate(max_iter=args.steps, flush_l2=True, **kw)
+    res = icp.estimate(max_iter=args.steps, flush_l2=not args.no_flush, **kw)
     ctx.synchronize()
     barrier(world)
     wall = time.perf_counter() - t0
@@ -241,13 +242,16 @@ def run_ours(args, w):
     # keep the GPUs busy a little longer for the clock sampler on very short runs; EVERY rank runs
     # it (the iteration contains a collective), the decision is taken on the max-over-ranks wall time
     clocks = None
+    # the same K iterations again with the events around the search kernel only (timing=2): the
+    # kernel's average duration for the roofline (one bracket per iteration at a time, see cb_icp_params)
+    resk = icp.estimate(max_iter=args.steps, flush_l2=not args.no_flush, timing=2, **kw)
     if cdist.max_over_ranks(wall) < 0.5:
-        icp.estimate(max_iter=max(args.steps, 50), flush_l2=False, **kw)
+        icp.estimate(max_iter=max(args.steps, 50), flush_l2=False, timing=0, **kw)
     if rank == 0:
         clocks = sampler.stop()
     assert res["iterations"] == args.steps
     ms_total = cdist.max_over_ranks(res["gpu_ms_total"])
-    ms_kernel = cdist.max_over_ranks(res["gpu_ms_search"])
+    ms_kernel = cdist.max_over_ranks(resk["gpu_ms_search"])
     ms_per_step = ms_total / args.steps
     its = 1e3 / ms_per_step
     value = its * n_src * world
@@ -263,13 +267,20 @@ def run_ours(args, w):
         barrier(world)
         t0 = time.perf_counter()
         c_dst = capi.Cloud(ctx, dst, nrm)
+        t1 = time.perf_counter()
         c_src = capi.Cloud(ctx, src, None, index_offset=lo)
-        c_icp = capi.Icp(ctx, c_dst, c_src)
-        r2 = c_icp.estimate(max_iter=e2e_iters, **kw)
+        t2 = time.perf_counter()
+        c_icp = capi.Icp(ctx, c_dst, c_src)  # builds both grid indices, means
+        t3 = time.perf_counter()
+        r2 = c_icp.estimate(max_iter=e2e_iters, timing=0, **kw)  # production settings: no event instrumentation
         T_host = np.array(r2["T"])  # result read back on the host
         ctx.synchronize()
+        t4 = time.perf_counter()
         barrier(world)
         e2e_t.append(time.perf_counter() - t0)
+        if rank == 0:
+            print(f"[e2e] upload dst {1e3 * (t1 - t0):.2f} ms, upload src {1e3 * (t2 - t1):.2f} ms, index+icp_create "
+                  f"{1e3 * (t3 - t2):.2f} ms, estimate({e2e_iters}) {1e3 * (t4 - t3):.2f} ms", file=sys.stderr)
         c_icp.close(); c_src.close(); c_dst.close()
     e2e_s = cdist.max_over_ranks(min(e2e_t))
     e2e_its = e2e_iters / e2e_s
@@ -341,6 +352,8 @@ def main():
 
     ap.add_argument("--workload", default="icp_p2p_1m", choices=sorted(WORKLOADS) + sorted(AUX))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true",
+                    help="experiments only: skip the L2 flush between timed iterations (the reported config says so)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.workload in AUX:  # secondary single-GPU workloads (k-means, RANSAC, PCA): bench_aux.py

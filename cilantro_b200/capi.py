@@ -33,6 +33,7 @@ class IcpParams(C.Structure):
         ("opt_tol", C.c_float),
         ("T_init", C.c_float * 12),
         ("flush_l2", C.c_int32),
+        ("timing", C.c_int32),
     ]
 
 
@@ -69,7 +70,7 @@ EXPORTED = [
     "cb_last_error", "cb_version",
     "cb_context_create", "cb_context_destroy", "cb_context_synchronize", "cb_context_device_info",
     "cb_context_kernel_launches", "cb_context_flush_l2",
-    "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info",
+    "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
     "cb_knn1_radius", "cb_knn_radius", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
@@ -169,6 +170,15 @@ class Context:
         buf = C.create_string_buffer(unique_id, 128)
         _check(lib().cb_context_init_comm(self.h, buf, C.c_int(rank), C.c_int(world)))
 
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(lib().cb_comm_ipc_handle(self.h, buf))
+        return buf.raw
+
+    def ipc_attach(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        _check(lib().cb_comm_ipc_attach(self.h, buf))
+
     def comm_info(self):
         r, w = C.c_int(), C.c_int()
         _check(lib().cb_context_comm_info(self.h, C.byref(r), C.byref(w)))
@@ -259,7 +269,7 @@ def transform_points(ctx, T, xyz):
 
 
 def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5,
-               T_init=None, flush_l2=False):
+               T_init=None, flush_l2=False, timing=1):
     p = IcpParams()
     lib().cb_icp_default_params(C.byref(p))
     p.metric = 0 if metric == "p2p" else 1
@@ -273,6 +283,7 @@ def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=
     for i, v in enumerate(Ti.reshape(-1)):
         p.T_init[i] = float(v)
     p.flush_l2 = int(flush_l2)
+    p.timing = int(timing)
     return p
 
 

@@ -3,6 +3,8 @@
 #include "icp_kernels.cuh"
 #include "stats_kernels.cuh"
 #include "host_solve.hpp"
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <cfloat>
 #include <cmath>
@@ -45,6 +47,80 @@ int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out) 
   out->gpartials = ctx->d_partials + (size_t)blocks * nv;
   out->counters = ctx->d_counter;
   out->result = ctx->d_result;
+  std::memset(&out->ex, 0, sizeof(out->ex));  // fused exchange off unless the caller arms it
+  return CB_OK;
+}
+
+// ---- fused exchange: tables, arming, host wait -------------------------------------------------------
+static inline unsigned long long* xchg_flags(void* base) { return reinterpret_cast<unsigned long long*>(base); }
+static inline double* xchg_vals(void* base) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + kXchgFlagBytes);
+}
+
+// (re)build the two device pointer tables from ctx->peer_xchg[0..world)
+static int upload_peer_tables(cb_context* ctx) {
+  double* hv[kMaxRanks];
+  unsigned long long* hf[kMaxRanks];
+  for (int p = 0; p < kMaxRanks; ++p) {
+    void* base = (p < ctx->world && ctx->peer_xchg[p]) ? ctx->peer_xchg[p] : ctx->d_xchg;
+    hv[p] = xchg_vals(base);
+    hf[p] = xchg_flags(base);
+  }
+  CB_CUDA(cudaMemcpy(ctx->d_peer_vals, hv, sizeof(hv), cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(ctx->d_peer_flags, hf, sizeof(hf), cudaMemcpyHostToDevice));
+  return CB_OK;
+}
+
+static int setup_exchange(cb_context* ctx) {
+  CB_CUDA(cudaMalloc(&ctx->d_xchg, kXchgBytes));
+  CB_CUDA(cudaMemset(ctx->d_xchg, 0, kXchgBytes));
+  CB_CUDA(cudaMalloc(&ctx->d_peer_vals, kMaxRanks * sizeof(double*)));
+  CB_CUDA(cudaMalloc(&ctx->d_peer_flags, kMaxRanks * sizeof(unsigned long long*)));
+  CB_CUDA(cudaHostAlloc(&ctx->h_sync, (64 + 4 * 64) * sizeof(unsigned long long), cudaHostAllocMapped));
+  std::memset(ctx->h_sync, 0, (64 + 4 * 64) * sizeof(unsigned long long));
+  ctx->peer_xchg[0] = ctx->d_xchg;
+  CB_TRY(upload_peer_tables(ctx));
+  ctx->ex_ready = true;  // world == 1: no peers, host mailbox only
+  return CB_OK;
+}
+
+bool arm_exchange(cb_context* ctx, Exchange* ex) {
+  static const bool disabled = getenv("CB_NO_FUSED_EXCHANGE") != nullptr;  // A/B switch for measurements
+  if (!ctx->ex_ready || disabled) return false;
+  ex->enabled = 1;
+  ex->rank = ctx->rank;
+  ex->world = ctx->world;
+  ex->seq = ++ctx->seq;
+  ex->peer_vals = ctx->d_peer_vals;
+  ex->peer_flags = ctx->d_peer_flags;
+  ex->host_flag = ctx->h_sync;  // mapped pinned memory: same address on host and device (UVA)
+  ex->host_vals = reinterpret_cast<double*>(ctx->h_sync + 8);
+  // CB_TRACE_EXCHANGE=1: %globaltimer stamps of the last 64 passes in the mapped mailbox page
+  static const bool trace = getenv("CB_TRACE_EXCHANGE") != nullptr;
+  ex->trace = trace ? ctx->h_sync + 64 + 4 * (ctx->seq % 64) : nullptr;
+  return true;
+}
+
+int wait_exchange(cb_context* ctx, int count, double* out) {
+  volatile unsigned long long* flag = ctx->h_sync;
+  const unsigned long long want = ctx->seq;
+  unsigned long long spins = 0;
+  while (*flag != want) {
+    if ((++spins & 0x3ffffull) == 0) {  // every ~0.3 ms: make sure the stream has not faulted or finished without us
+      cudaError_t q = cudaStreamQuery(ctx->stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        set_error("kernel failed while waiting for the fused exchange: %s", cudaGetErrorString(q));
+        return CB_ERR_CUDA;
+      }
+      if (q == cudaSuccess && *flag != want) {
+        set_error("fused exchange: the pass finished without publishing its result");
+        return CB_ERR_CUDA;
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  const volatile double* v = reinterpret_cast<const volatile double*>(ctx->h_sync + 8);
+  for (int i = 0; i < count; i++) out[i] = v[i];
   return CB_OK;
 }
 
@@ -119,6 +195,7 @@ int cb_context_create(int device, cb_context** out) {
   CB_CUDA(cudaEventCreate(&ctx->ev0));
   CB_CUDA(cudaEventCreate(&ctx->ev1));
   CB_CUDA(cudaEventCreate(&ctx->ev2));
+  CB_TRY(setup_exchange(ctx));
   *out = ctx;
   return CB_OK;
 }
@@ -133,6 +210,12 @@ void cb_context_destroy(cb_context* ctx) {
   if (ctx->d_result) cudaFree(ctx->d_result);
   if (ctx->h_result) cudaFreeHost(ctx->h_result);
   if (ctx->d_flush) cudaFree(ctx->d_flush);
+  for (int p = 0; p < kMaxRanks; ++p)
+    if (ctx->peer_xchg[p] && ctx->peer_xchg[p] != ctx->d_xchg) cudaIpcCloseMemHandle(ctx->peer_xchg[p]);
+  if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+  if (ctx->d_peer_vals) cudaFree(ctx->d_peer_vals);
+  if (ctx->d_peer_flags) cudaFree(ctx->d_peer_flags);
+  if (ctx->h_sync) cudaFreeHost(ctx->h_sync);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -173,7 +256,53 @@ int cb_context_init_comm(cb_context* ctx, const void* id, int rank, int world) {
   CB_CHECK(ctx && id, CB_ERR_INVALID, "null argument");
   CB_CHECK(world >= 1 && rank >= 0 && rank < world, CB_ERR_INVALID, "bad rank/world");
   CB_CUDA(cudaSetDevice(ctx->device));
-  return nccl_init(ctx, id, rank, world);
+  CB_CHECK(world <= kMaxRanks, CB_ERR_UNSUPPORTED, "at most 16 ranks per communicator");
+  CB_TRY(nccl_init(ctx, id, rank, world));
+  // until cb_comm_ipc_attach() maps the peers' exchange tables, reductions go through NCCL
+  ctx->ex_ready = (world == 1);
+  return CB_OK;
+}
+
+int cb_comm_ipc_handle(cb_context* ctx, void* out_64_bytes) {
+  CB_CHECK(ctx && out_64_bytes, CB_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  CB_CUDA(cudaIpcGetMemHandle(&h, ctx->d_xchg));
+  std::memcpy(out_64_bytes, &h, sizeof(h));
+  return CB_OK;
+}
+
+int cb_comm_ipc_attach(cb_context* ctx, const void* handles) {
+  CB_CHECK(ctx && handles, CB_ERR_INVALID, "null argument");
+  CB_CHECK(ctx->world >= 1 && ctx->world <= kMaxRanks, CB_ERR_INVALID, "call cb_context_init_comm first");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int p = 0; p < ctx->world; ++p) {
+    if (p == ctx->rank) {
+      ctx->peer_xchg[p] = ctx->d_xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, reinterpret_cast<const char*>(handles) + 64 * (size_t)p, sizeof(h));
+    void* ptr = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      set_error("cudaIpcOpenMemHandle(rank %d) failed: %s (fused exchange unavailable, NCCL path stays active)", p,
+                cudaGetErrorString(e));
+      (void)cudaGetLastError();
+      return CB_ERR_CUDA;
+    }
+    ctx->peer_xchg[p] = ptr;
+  }
+  // The tables were zeroed when the context was created and are only ever written by passes with
+  // world > 1, so they are still zero here; do NOT clear them now — a faster peer may already be
+  // writing its first row. The launcher barriers after this call before the first pass anyway.
+  ctx->seq = 0;
+  ctx->h_sync[0] = 0;
+  CB_TRY(upload_peer_tables(ctx));
+  ctx->ex_ready = true;
+  return CB_OK;
 }
 
 int cb_context_comm_info(cb_context* ctx, int* rank, int* world) {
@@ -420,23 +549,26 @@ static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, 
   return CB_OK;
 }
 
+// Totals of the last reduction pass: through the fused exchange when the pass carried it (no stream
+// synchronisation: the host polls its mailbox), else all-reduce (NCCL) + copy + synchronise.
+static int icp_fetch(cb_context* ctx, int count, double* out) {
+  if (ctx->pass_armed) return wait_exchange(ctx, count, out);
+  return fetch_result(ctx, count, true, out);
+}
+
 // One estimator call of updateEstimate(): returns tform_iter (already un-centred), and the
-// correspondence count of the search pass.
-static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, float* Titer, double* n_corr) {
+// correspondence count of the search pass. k0/k1 (nullable) are recorded around the search kernel.
+static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, float* Titer, double* n_corr,
+                      cudaEvent_t k0, cudaEvent_t k1) {
   cb_context* ctx = icp->ctx;
   IcpArgs a;
   double sums[kMaxValues];
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
     CB_TRY(icp_fill_args(icp, prm, T, nullptr, false, &a));
-    CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
-    CB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    CB_TRY(fetch_result(ctx, kP2PValues, true, sums));
-    {
-      float ms = 0.f;
-      CB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-      icp->search_ms += ms;
-    }
+    if (k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
+    CB_TRY(icp_fetch(ctx, kP2PValues, sums));
     kabsch_from_moments(sums, Titer);
     *n_corr = sums[0];
     icp->nn_valid = true;
@@ -451,23 +583,18 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   // has_point_to_plane_terms && dst_p.cols() != dst_n.cols() -> return false with identity (:269-272)
   const bool bail_no_normals = w_pl_on && !dst_has_normals;
   const int max_opt = std::max(prm->max_opt_iter, 0);
-  bool any_pass = false;
   for (int it = 0; it < std::max(max_opt, 1); ++it) {
     CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1, &a));
     const bool search = (it == 0);
     // the first pass always runs (it is also the correspondence search of this ICP iteration)
-    if (search) CB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (search && k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
-    if (search) CB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    CB_TRY(fetch_result(ctx, kCombinedValues, true, sums));
+    if (search && k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
+    CB_TRY(icp_fetch(ctx, kCombinedValues, sums));
     if (search) {
-      float ms = 0.f;
-      CB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-      icp->search_ms += ms;
       *n_corr = sums[0];
       icp->nn_valid = true;
     }
-    any_pass = true;
     const bool has_terms = sums[0] > 0.0 && (w_pt_on || w_pl_on);
     if (!has_terms || bail_no_normals) {
       t34_identity(Titer);
@@ -480,7 +607,6 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
     std::memcpy(Tin, Tnext, sizeof(Tin));
     if (dn < prm->opt_tol) break;  // :360-363
   }
-  (void)any_pass;
   std::memcpy(Titer, Tin, sizeof(Tin));
   float smt[3];
   apply_point(T, icp->src_mean, smt);
@@ -495,7 +621,13 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   CB_CUDA(cudaSetDevice(ctx->device));
   const uint64_t launches0 = ctx->launches;
   const int max_iter = std::max(prm->max_iter, 0);
-  while ((int)icp->events.size() < 2 * max_iter) {
+  // Optional CUDA-event instrumentation, ONE bracket (2 events) per iteration: timing 1 = whole
+  // iteration, timing 2 = the search kernel only. Every cudaEventRecord costs the device front end a
+  // few microseconds — measured with %globaltimer: 4 records per iteration inflated a 103 us period to
+  // 147 us — so production runs (timing 0) record nothing. Elapsed times are read after the final
+  // synchronise: with the fused exchange the host never waits on the stream inside the loop.
+  const int timing = prm->timing;
+  while (timing != 0 && (int)icp->events.size() < 2 * max_iter) {
     cudaEvent_t e;
     CB_CUDA(cudaEventCreate(&e));
     icp->events.push_back(e);
@@ -509,26 +641,44 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   icp->search_ms = 0;
   while (iters < max_iter) {  // icp_base.hpp:76-84
     if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
-    CB_CUDA(cudaEventRecord(icp->events[2 * iters], ctx->stream));
+    cudaEvent_t e0 = timing ? icp->events[2 * iters] : nullptr, e1 = timing ? icp->events[2 * iters + 1] : nullptr;
+    if (timing == 1) CB_CUDA(cudaEventRecord(e0, ctx->stream));
     float Titer[12];
     // updateCorrespondences() + updateEstimate(): one fused pass (+ stored-correspondence passes
-    // for inner Gauss-Newton iterations), reduction, host solve
-    CB_TRY(icp_update(icp, prm, T, Titer, &n_corr));
-    CB_CUDA(cudaEventRecord(icp->events[2 * iters + 1], ctx->stream));
+    // for inner Gauss-Newton iterations), reduction (+ exchange), host solve
+    CB_TRY(icp_update(icp, prm, T, Titer, &n_corr, timing == 2 ? e0 : nullptr, timing == 2 ? e1 : nullptr));
     reorthonormalize(Titer);           // :207-211
     compose(Titer, T, T);              // :213
     last_delta = update_norm(Titer);   // :214-216
+    // recorded AFTER the host solve: the device timestamps it when it gets to it, so the bracket
+    // covers kernel + exchange + host solve of this iteration
+    if (timing == 1) CB_CUDA(cudaEventRecord(e1, ctx->stream));
     iters++;
     if (last_delta < prm->tol) break;  // icp_base.hpp:83
   }
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   icp->iter_ms.assign(iters, 0.0);
   double total = 0;
-  for (int i = 0; i < iters; i++) {
+  for (int i = 0; i < iters && timing != 0; i++) {
     float ms = 0.f;
     CB_CUDA(cudaEventElapsedTime(&ms, icp->events[2 * i], icp->events[2 * i + 1]));
-    icp->iter_ms[i] = ms;
-    total += ms;
+    if (timing == 1) {
+      icp->iter_ms[i] = ms;
+      total += ms;
+    } else {
+      icp->search_ms += ms;
+    }
+  }
+  if (getenv("CB_TRACE_EXCHANGE") && ctx->seq >= 8) {
+    // last 6 passes: kernel start -> local reduction -> peers summed -> mailbox flag, and start-to-start period
+    unsigned long long prev0 = 0;
+    for (unsigned long long q = ctx->seq - 5; q <= ctx->seq; ++q) {
+      const unsigned long long* t = ctx->h_sync + 64 + 4 * (q % 64);
+      fprintf(stderr, "[rank %d pass %llu] start->reduced %.1f us, reduced->peers %.1f us, peers->flag %.1f us, period %.1f us\n",
+              ctx->rank, q, (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3,
+              prev0 ? (t[0] - prev0) * 1e-3 : 0.0);
+      prev0 = t[0];
+    }
   }
   std::memcpy(res->T, T, sizeof(T));
   res->iterations = iters;
@@ -565,7 +715,7 @@ int cb_icp_accumulate(cb_icp* icp, const cb_icp_params* prm, const float* T12, d
     CB_TRY(launch_icp_pass(ctx, a, kModeCombined, true, prm->w_pt > 0.f, prm->w_pl > 0.f));
   }
   CB_CHECK(cap >= nv, CB_ERR_INVALID, "sums buffer too small");
-  CB_TRY(fetch_result(ctx, nv, true, tmp));
+  CB_TRY(icp_fetch(ctx, nv, tmp));
   std::memcpy(sums, tmp, nv * sizeof(double));
   icp->nn_valid = true;
   return nv;

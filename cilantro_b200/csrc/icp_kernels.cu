@@ -47,7 +47,10 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
   // compact spatial neighbourhood (L1 reuse of the reference cells).
   __shared__ WarpSearchSmem wsm[SEARCH ? kBlock / 32 : 1];
   __shared__ AsyncReduceSmem<NV> rsm;
-  if constexpr (MODE != kModeKnn) async_reduce_init(rsm);
+  if constexpr (MODE != kModeKnn) {
+    if (a.rs.ex.trace && blockIdx.x == 0 && threadIdx.x == 0) a.rs.ex.trace[0] = global_timer_ns();  // kernel start
+    async_reduce_init(rsm);
+  }
   if (SEARCH && threadIdx.x == 0 && a.dst.n > 0) {
     // Software prefetch of the reference arrays into L2, a fixed number of blocks ahead of the
     // consumer front. Both clouds are cell-sorted x-major in (nearly) the same frame, so block b of
@@ -239,6 +242,8 @@ int launch_icp_pass(cb_context* ctx, const IcpArgs& a, int mode, bool search, bo
   const int blocks = std::max(1, (int)((a.n_src + kBlock - 1) / kBlock));
   IcpArgs args = a;
   CB_TRY(get_reduce_scratch(ctx, blocks, kMaxValues, &args.rs));
+  // reduction passes carry the fused NVLink all-reduce + host mailbox epilogue when the context has it
+  ctx->pass_armed = (mode != kModeKnn) && arm_exchange(ctx, &args.rs.ex);
   {
     // ~2 waves of resident blocks; CB_PREFETCH_BLOCKS overrides it for experiments
     static const int env_pf = [] {

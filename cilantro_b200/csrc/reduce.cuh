@@ -94,10 +94,10 @@ __device__ __forceinline__ void async_reduce_init(AsyncReduceSmem<NV>& sm) {
 
 // one warp sums rows r0..r1-1 of a [rows][NV] table (lane i owns value i; NV <= 32), 8 loads in flight
 template <int NV>
-__device__ __forceinline__ void warp_sum_rows(const double* __restrict__ table, unsigned int r0, unsigned int r1,
-                                              double* __restrict__ out, int lane) {
+__device__ __forceinline__ double warp_sum_rows(const double* __restrict__ table, unsigned int r0, unsigned int r1,
+                                                int lane) {
+  double s = 0;
   if (lane < NV) {
-    double s = 0;
     unsigned int b = r0;
     for (; b + 8 <= r1; b += 8) {
       double t[8];
@@ -107,8 +107,62 @@ __device__ __forceinline__ void warp_sum_rows(const double* __restrict__ table, 
       for (int u = 0; u < 8; u++) s += t[u];
     }
     for (; b < r1; ++b) s += __ldcg(table + (size_t)b * NV + lane);
-    out[lane] = s;
   }
+  return s;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused collective + host notification (struct Exchange, cb_internal.hpp). Called by ONE warp per
+// GPU and pass, lane i < NV holding this GPU's total of value i. Returns the cross-rank total.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int NV>
+__device__ __forceinline__ double exchange_and_publish(double s, const ReduceScratch& rs, int lane) {
+  const Exchange& ex = rs.ex;
+  if (ex.enabled) {
+    const int par = (int)(ex.seq & 1ull);
+    if (ex.trace && lane == 0) ex.trace[1] = global_timer_ns();  // local reduction done
+    if (ex.world > 1) {
+      // 1. my row -> every rank's table (remote stores over NVLink), then a release flag per rank
+      if (lane < NV)
+        for (int p = 0; p < ex.world; ++p) ex.peer_vals[p][(par * ex.world + ex.rank) * kExchangeVals + lane] = s;
+      __threadfence_system();
+      __syncwarp();
+      if (lane < ex.world) st_release_sys(ex.peer_flags[lane] + par * ex.world + ex.rank, ex.seq);
+      // 2. wait until every rank's row of THIS pass has landed in my table (lane r watches rank r)
+      if (lane < ex.world) {
+        const unsigned long long* f = ex.peer_flags[ex.rank] + par * ex.world + lane;
+        while (ld_acquire_sys(f) != ex.seq) {
+        }
+      }
+      __syncwarp();
+      // 3. identical fixed-order sum on every rank -> bit-identical totals, no broadcast needed
+      if (lane < NV) {
+        const volatile double* rows = ex.peer_vals[ex.rank] + (size_t)par * ex.world * kExchangeVals;
+        s = 0;
+        for (int r = 0; r < ex.world; ++r) s += rows[r * kExchangeVals + lane];
+      }
+    }
+    if (ex.trace && lane == 0) ex.trace[2] = global_timer_ns();  // peers' rows received and summed
+    if (lane < NV) ex.host_vals[lane] = s;
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) st_release_sys(ex.host_flag, ex.seq);
+    if (ex.trace && lane == 0) ex.trace[3] = global_timer_ns();  // host mailbox flag written
+  }
+  return s;
 }
 
 // Sum NP (16 or 32) per-lane values over the 32 lanes of a warp with a transposing butterfly:
@@ -176,7 +230,10 @@ __device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const Reduc
   t = __shfl_sync(0xffffffffu, t, 0);
   if (t != (g1 - g0) - 1) return;
   __threadfence();
-  warp_sum_rows<NV>(rs.partials, g0, g1, rs.gpartials + (size_t)g * NV, lane);
+  {
+    const double gs = warp_sum_rows<NV>(rs.partials, g0, g1, lane);
+    if (lane < NV) rs.gpartials[(size_t)g * NV + lane] = gs;
+  }
   if (lane == 0) rs.counters[1 + g] = 0;
   __threadfence();
   __syncwarp();
@@ -184,8 +241,12 @@ __device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const Reduc
   t = __shfl_sync(0xffffffffu, t, 0);
   if (t != ngroups - 1) return;
   __threadfence();
-  warp_sum_rows<NV>(rs.gpartials, 0, ngroups, rs.result, lane);
+  // the last warp of the grid: this GPU's totals -> (optional) fused all-reduce over NVLink peer
+  // memory -> device result + mapped host mailbox
+  double tot = warp_sum_rows<NV>(rs.gpartials, 0, ngroups, lane);
   if (lane == 0) rs.counters[0] = 0;
+  tot = exchange_and_publish<NV>(tot, rs, lane);
+  if (lane < NV) rs.result[lane] = tot;
 }
 
 }  // namespace cb

@@ -60,7 +60,34 @@ def attach_comm(ctx):
     uid = capi.comm_unique_id() if rank == 0 else None
     uid = broadcast_bytes(uid, 0)
     ctx.init_comm(uid, rank, world)
+    # fused exchange over NVLink peer memory: all-gather the CUDA-IPC handles, map the peers' tables.
+    # All ranks must take the same path, so the outcome is agreed on before anyone proceeds.
+    if os.environ.get("CB_NO_FUSED_EXCHANGE") is None:
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.ipc_handle())
+        ok = 1
+        try:
+            ctx.ipc_attach(b"".join(handles))
+        except capi.CbError:
+            ok = 0
+        if min_over_ranks(ok) == 0:
+            raise RuntimeError("fused exchange could not be mapped on every rank; set CB_NO_FUSED_EXCHANGE=1 "
+                               "to use the NCCL all-reduce path")
+    dist.barrier()
     return rank, world
+
+
+def min_over_ranks(x):
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return x
+    t = torch.tensor([float(x)], dtype=torch.float64)
+    if dist.get_backend() == "nccl":
+        t = t.cuda()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return t.item()
 
 
 def allreduce_sum_f64(values):

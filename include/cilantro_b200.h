@@ -69,6 +69,15 @@ int cb_context_flush_l2(cb_context* ctx);
 int cb_comm_unique_id(void* out_128_bytes);
 int cb_context_init_comm(cb_context* ctx, const void* unique_id_128_bytes, int rank, int world);
 int cb_context_comm_info(cb_context* ctx, int* rank, int* world);
+/* Optional, after cb_context_init_comm: the FUSED exchange. Every rank exports a 64-byte CUDA-IPC
+ * handle of its exchange table (cb_comm_ipc_handle), the launcher all-gathers them in rank order
+ * (world x 64 bytes) and every rank maps its peers' tables (cb_comm_ipc_attach), then barriers.
+ * From then on the ICP accumulation kernel itself all-reduces the 16/28 moments by writing them
+ * straight into the peers' tables over NVLink and publishes the total to a mapped host mailbox, so an
+ * iteration costs one kernel + one host poll: no ncclAllReduce, cudaMemcpy or stream synchronise.
+ * If mapping fails (no peer access) the call returns an error and the NCCL path stays active. */
+int cb_comm_ipc_handle(cb_context* ctx, void* out_64_bytes);
+int cb_comm_ipc_attach(cb_context* ctx, const void* handles_world_x_64_bytes);
 
 /* ---- device-resident point sets --------------------------------------------------------------
  * Replaces: PointFeaturesAdaptor<float,3> ctor (correspondence_search/
@@ -134,6 +143,10 @@ typedef struct cb_icp_params {
   float opt_tol;        /* :45, default 1e-5 */
   float T_init[12];     /* icp_base.hpp:58-61 */
   int32_t flush_l2;     /* bench hygiene: evict L2 before every iteration (outside the timed events) */
+  int32_t timing;       /* CUDA-event instrumentation of estimate(): 0 none (production), 1 one bracket per
+                           iteration (kernel + exchange + host solve) -> gpu_ms_total / cb_icp_iteration_times,
+                           2 one bracket per search kernel -> gpu_ms_search. Each cudaEventRecord costs a few us of
+                           device front-end time, comparable to the ~100 us iteration, hence one mode at a time. */
 } cb_icp_params;
 
 typedef struct cb_icp_result {
