@@ -8,8 +8,10 @@ moment accumulation + reduction + host solve) on the named workload. At N = 1 th
 BASELINE.json configs[1]: 1 M -> 1 M synthetic uniform clouds, point-to-point metric, k = 1.
 For N > 1 (one process per GPU under torchrun) the job is weak-scaled: every rank owns 1 M source
 points, the destination cloud (N M points) is replicated, and the only exchange per iteration is the
-library's own NCCL all-reduce of the 16 Kabsch moments. `value` counts correspondences (source points
-processed) per second over ALL ranks; iterations/s is reported next to it.
+all-reduce of the 16 Kabsch moments, fused into the accumulation kernel's epilogue (rows written straight
+into the peers' tables over NVLink peer memory; CB_NO_FUSED_EXCHANGE=1 selects the ncclAllReduce path).
+`value` counts correspondences (source points processed) per second over ALL ranks; iterations/s is
+reported next to it.
 
 Timing: W untimed warm-up iterations, then K timed iterations bracketed by barrier + synchronize;
 each iteration is timed on the device with CUDA events inside the library (cb_icp_estimate), with an
@@ -74,7 +76,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -142,12 +144,25 @@ def cpu_reference_run(w, steps, warmup, dst, src, nrm, build_in_timed_region):
 
     oracle.build()
     kind = "reference" if oracle.have_ref() else "port"
-    cores = oracle.num_threads()
     mk = (lambda: oracle.RefKnn(dst)) if oracle.have_ref() else (lambda: oracle.BruteKnn(dst))
     kw = dict(metric=w["metric"], dst_n=nrm, tol=0.0, max_d2=np.float32(w["max_d2"]), parallel=True, **w["kw"])
     t0 = time.perf_counter()
     knn = mk()
     t_build = time.perf_counter() - t0
+    # "all the host threads it can use": the kd-tree sweep is latency-bound and was measured 3x slower
+    # with every hyper-thread (128) than with one thread per core (64) on the B200 host, so probe both
+    # on one iteration and give the reference the better setting
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    best = None
+    for nt in sorted({ncpu, max(1, ncpu // 2)}):
+        oracle.set_num_threads(nt)
+        t0 = time.perf_counter()
+        oracle.icp(dst, src, knn, max_iter=1, **kw)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    oracle.set_num_threads(best[1])
+    cores = best[1]
     if warmup > 0:
         oracle.icp(dst, src, knn, max_iter=warmup, **kw)
     t0 = time.perf_counter()
@@ -196,7 +211,9 @@ def workload_config(args, w, world, n_src_rank, n_dst):
         "workload": (f"{args.workload}: rigid ICP, {w['metric']} metric, k=1, {n_src_rank} source points per GPU x {world} "
                      f"GPU(s) against {n_dst} destination points (uniform random in the unit cube, seed 1, "
                      f"noise +-0.001), max_distance^2={w['max_d2']:g}, fixed iteration count (tol=0)"),
-        "parallelism": f"src sharded x{world}, dst replicated, one 16-value (p2p) / 28-value NCCL all-reduce per iteration",
+        "parallelism": (f"src sharded x{world}, dst replicated, one 16-value (p2p) / 28-value all-reduce per iteration, "
+                        + ("ncclAllReduce" if os.environ.get("CB_NO_FUSED_EXCHANGE") else
+                           "fused into the kernel epilogue over NVLink peer memory")),
         "l2": ("NOT flushed (--no-flush experiment; inputs smaller than L2 stay resident)" if getattr(args, "no_flush", False)
                else "flushed before every timed iteration (256 MiB memset outside the CUDA-event bracket)"),
     }

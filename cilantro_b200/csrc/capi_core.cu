@@ -189,6 +189,15 @@ int cb_context_create(int device, cb_context** out) {
   ctx->hbm_bytes = prop.totalGlobalMem;
   snprintf(ctx->name, sizeof(ctx->name), "%s", prop.name);
   CB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  {
+    // All cloud / index / scratch buffers come from the stream-ordered pool. Keep freed memory in the
+    // pool (default: returned to the OS at every synchronise, which made repeated cloud creation pay
+    // page allocation again each time: 30-400 ms outliers in the end-to-end call).
+    cudaMemPool_t pool;
+    CB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    CB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CB_CUDA(cudaMalloc(&ctx->d_result, 64 * sizeof(double)));
   CB_CUDA(cudaMemset(ctx->d_result, 0, 64 * sizeof(double)));
   CB_CUDA(cudaMallocHost(&ctx->h_result, 64 * sizeof(double)));
@@ -324,10 +333,10 @@ static int cloud_create_common(cb_context* ctx, const float* xyz, const float* n
   c->n = n;
   c->index_offset = off;
   if (n > 0) {
-    CB_CUDA(cudaMalloc(&c->d_raw, 3 * n * sizeof(float)));
+    CB_CUDA(cudaMallocAsync(&c->d_raw, 3 * n * sizeof(float), ctx->stream));
     CB_CUDA(cudaMemcpyAsync(c->d_raw, xyz, 3 * n * sizeof(float), kind, ctx->stream));
     if (normals) {
-      CB_CUDA(cudaMalloc(&c->d_raw_nrm, 3 * n * sizeof(float)));
+      CB_CUDA(cudaMallocAsync(&c->d_raw_nrm, 3 * n * sizeof(float), ctx->stream));
       CB_CUDA(cudaMemcpyAsync(c->d_raw_nrm, normals, 3 * n * sizeof(float), kind, ctx->stream));
     }
     // the caller's buffers may be released as soon as this returns
@@ -351,11 +360,11 @@ void cb_cloud_destroy(cb_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->ctx->device);
   cudaStreamSynchronize(c->ctx->stream);
-  if (c->d_raw) cudaFree(c->d_raw);
-  if (c->d_raw_nrm) cudaFree(c->d_raw_nrm);
-  if (c->d_pts) cudaFree(c->d_pts);
-  if (c->d_nrm) cudaFree(c->d_nrm);
-  if (c->d_cell_start) cudaFree(c->d_cell_start);
+  if (c->d_raw) cudaFreeAsync(c->d_raw, c->ctx->stream);
+  if (c->d_raw_nrm) cudaFreeAsync(c->d_raw_nrm, c->ctx->stream);
+  if (c->d_pts) cudaFreeAsync(c->d_pts, c->ctx->stream);
+  if (c->d_nrm) cudaFreeAsync(c->d_nrm, c->ctx->stream);
+  if (c->d_cell_start) cudaFreeAsync(c->d_cell_start, c->ctx->stream);
   delete c;
 }
 
@@ -507,8 +516,8 @@ int cb_icp_create(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, cb_
   // dst is replicated on every rank, src is sharded: only the src mean needs the all-reduce
   CB_TRY(global_mean(ctx, dst, false, icp->dst_mean));
   CB_TRY(global_mean(ctx, src, true, icp->src_mean));
-  CB_CUDA(cudaMalloc(&icp->d_nn_pos, std::max<size_t>(src->n, 1) * sizeof(int)));
-  CB_CUDA(cudaMalloc(&icp->d_nn_d2, std::max<size_t>(src->n, 1) * sizeof(float)));
+  CB_CUDA(cudaMallocAsync(&icp->d_nn_pos, std::max<size_t>(src->n, 1) * sizeof(int), ctx->stream));
+  CB_CUDA(cudaMallocAsync(&icp->d_nn_d2, std::max<size_t>(src->n, 1) * sizeof(float), ctx->stream));
   *out = icp;
   return CB_OK;
 }
@@ -517,8 +526,8 @@ void cb_icp_destroy(cb_icp* icp) {
   if (!icp) return;
   cudaSetDevice(icp->ctx->device);
   cudaStreamSynchronize(icp->ctx->stream);
-  if (icp->d_nn_pos) cudaFree(icp->d_nn_pos);
-  if (icp->d_nn_d2) cudaFree(icp->d_nn_d2);
+  if (icp->d_nn_pos) cudaFreeAsync(icp->d_nn_pos, icp->ctx->stream);
+  if (icp->d_nn_d2) cudaFreeAsync(icp->d_nn_d2, icp->ctx->stream);
   for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
   delete icp;
 }

@@ -302,7 +302,7 @@ int ensure_index(cb_cloud* c) {
   if (n == 0) {
     c->nx = c->ny = c->nz = 1;
     c->h = c->inv_h = 1.f;
-    CB_CUDA(cudaMalloc(&c->d_cell_start, 2 * sizeof(uint32_t)));
+    CB_CUDA(cudaMallocAsync(&c->d_cell_start, 2 * sizeof(uint32_t), ctx->stream));
     CB_CUDA(cudaMemsetAsync(c->d_cell_start, 0, 2 * sizeof(uint32_t), ctx->stream));
     c->indexed = true;
     return CB_OK;
@@ -366,8 +366,8 @@ int ensure_index(cb_cloud* c) {
     gp.ny = dims[1];
     gp.nz = dims[2];
     ncells = (size_t)dims[0] * dims[1] * dims[2];
-    if (d_hist) CB_CUDA(cudaFree(d_hist));
-    CB_CUDA(cudaMalloc(&d_hist, (ncells + 1) * sizeof(uint32_t)));
+    if (d_hist) CB_CUDA(cudaFreeAsync(d_hist, ctx->stream));
+    CB_CUDA(cudaMallocAsync(&d_hist, (ncells + 1) * sizeof(uint32_t), ctx->stream));
     CB_CUDA(cudaMemsetAsync(d_hist, 0, (ncells + 1) * sizeof(uint32_t), ctx->stream));
     CB_CUDA(cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     hist_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(c->d_raw, n, gp, d_cell_id, d_hist);
@@ -417,8 +417,8 @@ int ensure_index(cb_cloud* c) {
                                                                                  d_big);
   sort_big_cells_kernel<<<ctx->sm_count * 2, kThreads, 0, ctx->stream>>>(d_hist, d_big + 1, d_big, d_perm, d_tmp);
   // 5. gather
-  CB_CUDA(cudaMalloc(&c->d_pts, n * sizeof(float4)));
-  if (c->d_raw_nrm) CB_CUDA(cudaMalloc(&c->d_nrm, n * sizeof(float4)));
+  CB_CUDA(cudaMallocAsync(&c->d_pts, n * sizeof(float4), ctx->stream));
+  if (c->d_raw_nrm) CB_CUDA(cudaMallocAsync(&c->d_nrm, n * sizeof(float4), ctx->stream));
   gather_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(c->d_raw, c->d_raw_nrm, d_perm, n, c->d_pts,
                                                                    c->d_nrm);
   ctx->launches += 4;
