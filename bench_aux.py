@@ -162,6 +162,63 @@ def pca(args, n=50_000_000):
     print(json.dumps(line))
 
 
-AUX = {"kmeans_50m": kmeans, "ransac_5m": ransac, "pca_50m": pca,
+def normals(args, n=5_000_000, k=10):
+    """PointCloud3f::estimateNormalsKNN(k) (view point = origin) on a synthetic scanned sheet."""
+    import oracle
+    from cilantro_b200 import synth
+    from bench import load_peaks
+
+    capi, ctx = _ctx()
+    pts, _ = synth.surface_cloud(n, seed=1, noise=0.0005)
+    cloud = capi.Cloud(ctx, pts)
+    vp = [0.0, 0.0, 0.0]
+    for _ in range(max(args.warmup, 1)):
+        cloud.estimate_normals(k=k, view_point=vp, fetch=False)
+    l0 = ctx.kernel_launches()
+    ms_list = []
+    for _ in range(args.steps):
+        ctx.flush_l2()
+        ms_list.append(cloud.estimate_normals(k=k, view_point=vp, fetch=False)["gpu_ms"])
+    launches = ctx.kernel_launches() - l0
+    ms = float(np.mean(ms_list))
+    # e2e: host points -> upload -> grid -> normals -> normals on host
+    e2e = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        c2 = capi.Cloud(ctx, pts)
+        c2.estimate_normals(k=k, view_point=vp, want_curvature=False)
+        e2e.append(time.perf_counter() - t0)
+        c2.close()
+    e2e_s = min(e2e)
+    peak, src = load_peaks()
+    sample = min(n, 2_000_000)
+    knn = oracle.make_knn(pts[:sample])
+    t0 = time.perf_counter()
+    oracle.estimate_normals(pts[:sample], knn, k=k, view_point=vp)
+    cpu_s = time.perf_counter() - t0
+    algo = 28.0 * n  # read float4 point once + write one 12 B normal (the cell-sorted float4 copy is internal)
+    line = {
+        "metric": "normal_estimation_points_per_sec", "value": n * 1e3 / ms, "unit": "points/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"PointCloud3f::estimateNormalsKNN({k}) on a {n}-point noisy sheet, view point = origin",
+                   "l2": "flushed before every timed call"},
+        "e2e": {"value": n / e2e_s, "unit": "points/s", "h2d_bytes_per_step": pts.nbytes, "d2h_bytes_per_step": 12 * n,
+                "what": f"cb_cloud_create + cb_cloud_estimate_normals + normals on host: {e2e_s * 1e3:.1f} ms"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": algo / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "normals_knn_kernel",
+                     "peak_source": src, "note": "28 B/point algorithmic; the kernel is bound by the k-best search "
+                     "(instruction issue), not by HBM"},
+        "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": oracle.num_threads(),
+                         "kind": "reference" if knn.kind == "reference" else "port",
+                         "sample": f"kNN (reference nanoflann, OpenMP) + covariance + eigen on {sample} points; "
+                                   "kd-tree build not included"},
+    }
+    print(json.dumps(line))
+
+
+AUX = {"normals_5m": normals, "normals_1m": lambda a: normals(a, n=1_000_000),
+       "kmeans_50m": kmeans, "ransac_5m": ransac, "pca_50m": pca,
        "kmeans_5m": lambda a: kmeans(a, n=5_000_000, k=256), "ransac_500k": lambda a: ransac(a, n=500_000, batch=256),
        "pca_5m": lambda a: pca(a, n=5_000_000)}

@@ -72,6 +72,7 @@ EXPORTED = [
     "cb_context_kernel_launches", "cb_context_flush_l2",
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
+    "cb_cloud_estimate_normals",
     "cb_knn1_radius", "cb_knn_radius", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
     "cb_icp_correspondences", "cb_icp_residuals", "cb_icp_accumulate",
@@ -223,6 +224,20 @@ class Cloud:
             self.close()
         except Exception:
             pass
+
+    def estimate_normals(self, k=0, radius2=0.0, view_point=None, use_current_as_ref=False, want_curvature=True,
+                         want_cov=False, fetch=True):
+        """cb_cloud_estimate_normals: kNN (k>0), kNN-in-radius (k>0, radius2>0) or radius (k=0) neighbourhoods.
+        Stores the normals in the cloud; returns dict(normals, curvature, cov6, gpu_ms)."""
+        n = self.n
+        nrm = np.empty((n, 3), np.float32) if fetch else None
+        curv = np.empty(n, np.float32) if (fetch and want_curvature) else None
+        cov = np.empty((n, 6), np.float32) if (fetch and want_cov) else None
+        vp = None if view_point is None else np.ascontiguousarray(view_point, np.float32).reshape(3)
+        ms = C.c_float()
+        _check(lib().cb_cloud_estimate_normals(self.ctx.h, self.h, C.c_int(k), C.c_float(radius2), _p(vp),
+                                               C.c_int(int(use_current_as_ref)), _p(nrm), _p(curv), _p(cov), C.byref(ms)))
+        return {"normals": nrm, "curvature": curv, "cov6": cov, "gpu_ms": ms.value}
 
     def grid_info(self):
         edge = C.c_float()

@@ -3,7 +3,7 @@
 // same shell sweep as nn_search.cuh, with a per-thread sorted list of the k best (d2, index) pairs
 // whose worst entry plays the role of nanoflann's worstDist() (kd_tree.hpp:101).
 #include "cb_internal.hpp"
-#include "nn_search.cuh"
+#include "grid_sweep.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -63,56 +63,7 @@ __global__ void __launch_bounds__(kBlock) knn_k_kernel(const GridView g, const f
         if (r < max_d2) kbest_insert<K>(bd, bi, k, count, r, __float_as_int(p.w));
       }
     };
-    if (g.n > 0) {
-      const float fx = cell_coord(qx, g.ox, g.inv_h), fy = cell_coord(qy, g.oy, g.inv_h),
-                  fz = cell_coord(qz, g.oz, g.inv_h);
-      const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);
-      const float hs2 = g.h_safe * g.h_safe;
-      int k0 = 0;
-      k0 = max(k0, cx < 0 ? -cx : (cx > g.nx - 1 ? cx - (g.nx - 1) : 0));
-      k0 = max(k0, cy < 0 ? -cy : (cy > g.ny - 1 ? cy - (g.ny - 1) : 0));
-      k0 = max(k0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
-      for (int sh = k0;; ++sh) {
-        if (sh > k0 || sh > 0) {
-          // termination: nearest unscanned face vs the k-th best (ties beyond the face cannot
-          // enter: their distance is strictly larger than the bound, see nn_search.cuh)
-          const int kk = sh - 1;
-          float cover = 3.0e38f;
-          bool any = false;
-          if (cx - kk > 0) { cover = fminf(cover, fx - (float)(cx - kk)); any = true; }
-          if (cx + kk < g.nx - 1) { cover = fminf(cover, (float)(cx + kk + 1) - fx); any = true; }
-          if (cy - kk > 0) { cover = fminf(cover, fy - (float)(cy - kk)); any = true; }
-          if (cy + kk < g.ny - 1) { cover = fminf(cover, (float)(cy + kk + 1) - fy); any = true; }
-          if (cz - kk > 0) { cover = fminf(cover, fz - (float)(cz - kk)); any = true; }
-          if (cz + kk < g.nz - 1) { cover = fminf(cover, (float)(cz + kk + 1) - fz); any = true; }
-          if (!any) break;
-          cover -= kCellMargin;
-          if (cover > 0.f && cover * cover * hs2 >= bound()) break;
-        }
-        const int z0 = max(cz - sh, 0), z1 = min(cz + sh, g.nz - 1);
-        const int y0 = max(cy - sh, 0), y1 = min(cy + sh, g.ny - 1);
-        const int xl = cx - sh, xr = cx + sh;
-        const int x0 = max(xl, 0), x1 = min(xr, g.nx - 1);
-        for (int rz = z0; rz <= z1; ++rz) {
-          const float gz = slab_gap(fz, cz, rz);
-          if (gz * gz * hs2 >= bound()) continue;
-          const bool zshell = (rz - cz == sh) || (cz - rz == sh);
-          for (int ry = y0; ry <= y1; ++ry) {
-            const float gy = slab_gap(fy, cy, ry);
-            const float gyz2 = gy * gy + gz * gz;
-            if (gyz2 * hs2 >= bound()) continue;
-            const uint32_t base = ((uint32_t)rz * (uint32_t)g.ny + (uint32_t)ry) * (uint32_t)g.nx;
-            if (zshell || (ry - cy == sh) || (cy - ry == sh)) {
-              if (x0 <= x1) scan(__ldg(g.cell_start + base + x0), __ldg(g.cell_start + base + x1 + 1));
-            } else {
-              if (xl >= 0 && xl < g.nx) scan(__ldg(g.cell_start + base + xl), __ldg(g.cell_start + base + xl + 1));
-              if (sh > 0 && xr >= 0 && xr < g.nx)
-                scan(__ldg(g.cell_start + base + xr), __ldg(g.cell_start + base + xr + 1));
-            }
-          }
-        }
-      }
-    }
+    grid_sweep(g, qx, qy, qz, bound, scan);
     for (int j = 0; j < k; j++) {
       out_idx[(size_t)oi * k + j] = (j < count) ? bi[j] : -1;
       out_d2[(size_t)oi * k + j] = (j < count) ? bd[j] : max_d2;

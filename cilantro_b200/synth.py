@@ -67,6 +67,18 @@ def icp_pair(n, seed=1, noise=0.001, with_normals=False, n_src=None, T_ref=None)
     return dst, src, nrm, T_ref
 
 
+def surface_cloud(n, seed=1, noise=0.0005):
+    """A scanned-surface stand-in: the sheet z = 0.5 + 0.1 sin(6x) cos(5y) over [0,1)^2, sampled uniformly in
+    (x, y) with Gaussian noise along z. Returns points (n,3) float32 and the analytic unit normals (n,3), +z side."""
+    rng = np.random.default_rng(seed)
+    xy = rng.random((n, 2))
+    x, y = xy[:, 0], xy[:, 1]
+    z = 0.5 + 0.1 * np.sin(6 * x) * np.cos(5 * y) + noise * rng.standard_normal(n)
+    g = np.stack([-0.6 * np.cos(6 * x) * np.cos(5 * y), 0.5 * np.sin(6 * x) * np.sin(5 * y), np.ones(n)], axis=1)
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    return np.stack([x, y, z], axis=1).astype(np.float32), g.astype(np.float32)
+
+
 def kmeans_data(n, k, seed=1):
     """uniform [0,1)^3 points; initial centroids = first k points of a seeded shuffle (config 4)."""
     rng = np.random.default_rng(seed)

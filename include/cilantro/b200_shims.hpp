@@ -202,9 +202,15 @@ struct CloudHandle {
   cb_cloud* h = nullptr;
   CloudHandle() = default;
   CloudHandle(const ConstVectorSetMatrixMap3f& pts, const ConstVectorSetMatrixMap3f* normals = nullptr) {
+    reset(pts, normals);
+  }
+  void reset(const ConstVectorSetMatrixMap3f& pts, const ConstVectorSetMatrixMap3f* normals = nullptr) {
+    if (h) cb_cloud_destroy(h);
+    h = nullptr;
     const float* n = (normals && normals->cols() == pts.cols() && pts.cols() > 0) ? normals->data() : nullptr;
     check(cb_cloud_create(Context::get(), pts.data(), n, pts.cols(), 0, &h), "cb_cloud_create");
   }
+  CloudHandle(CloudHandle&& o) noexcept : h(o.h) { o.h = nullptr; }
   CloudHandle(const CloudHandle&) = delete;
   CloudHandle& operator=(const CloudHandle&) = delete;
   ~CloudHandle() {
@@ -225,7 +231,7 @@ public:
   using NeighborhoodSetResult = std::vector<NeighborhoodResult>;
 
   KDTree3f(const ConstVectorSetMatrixMap3f& data, size_t /*max_leaf_size*/ = 10, size_t /*num_build_threads*/ = 1)
-      : n_(data.cols()), cloud_(data) {}
+      : n_(data.cols()), data_map_(data), cloud_(data) {}
 
   bool isEmpty() const { return n_ == 0; }
 
@@ -275,9 +281,11 @@ public:
     }
     return out;
   }
+  const ConstVectorSetMatrixMap3f& getPointsMatrixMap() const { return data_map_; }  // core/kd_tree.hpp:172-174
 
 private:
   size_t n_;
+  ConstVectorSetMatrixMap3f data_map_;
   b200::CloudHandle cloud_;
 };
 
@@ -606,8 +614,155 @@ private:
 };
 
 // ---- PointCloud3f ------------------------------------------------------------------------------------------
+// ---- normal estimation (core/normal_estimation.hpp:11-421) ------------------------------------------
+// Same call surface as NormalEstimation<float,3>: neighbourhoods over the cloud itself; radii are
+// squared distances; fewer than 3 neighbours -> NaN; view point (default: none, :24-25) orients the
+// normals; reference normals (setReferenceNormals, :63-69) take precedence over it (:281-291).
+class NormalEstimation3f {
+public:
+  NormalEstimation3f(const ConstVectorSetMatrixMap3f& points, size_t /*max_leaf_size*/ = 10)
+      : n_(points.cols()), points_(points), cloud_(points) {
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    view_point_ = Vector3f(nan, nan, nan);
+  }
+  // from an existing search tree (:30-39): the same points; the device grid is rebuilt for this object
+  template <typename IndexT>
+  explicit NormalEstimation3f(const KDTree3f<IndexT>& kd_tree) : NormalEstimation3f(kd_tree.getPointsMatrixMap()) {}
+  // getNormals* (:71-81 and the Radius / KNNInRadius twins): return by value
+  VectorSet3f getNormalsKNN(size_t k) const { return estimateNormalsKNN(k); }
+  VectorSet3f getNormalsRadius(float radius) const { return estimateNormalsRadius(radius); }
+  VectorSet3f getNormalsKNNInRadius(size_t k, float radius) const { return estimateNormalsKNNInRadius(k, radius); }
+  const Vector3f& getViewPoint() const { return view_point_; }
+  NormalEstimation3f& setViewPoint(const Vector3f& vp) {  // :52-56
+    view_point_ = vp;
+    return *this;
+  }
+  NormalEstimation3f& setReferenceNormals(const ConstVectorSetMatrixMap3f& ref_normals) {  // :63-69
+    if (ref_normals.cols() == n_) {  // a copy: the caller may pass the very buffer the result goes to
+      ref_normals_.assign(ref_normals.data(), ref_normals.data() + 3 * n_);
+      use_ref_ = n_ > 0;
+    }
+    return *this;
+  }
+  // kNN (:83-129)
+  const NormalEstimation3f& estimateNormalsAndCurvatureKNN(VectorSet3f& normals, std::vector<float>& curvature,
+                                                           size_t k) const {
+    return run(&normals, &curvature, k, 0.f);
+  }
+  const NormalEstimation3f& estimateNormalsKNN(VectorSet3f& normals, size_t k) const {
+    return run(&normals, nullptr, k, 0.f);
+  }
+  VectorSet3f estimateNormalsKNN(size_t k) const {
+    VectorSet3f n;
+    run(&n, nullptr, k, 0.f);
+    return n;
+  }
+  const NormalEstimation3f& estimateCurvatureKNN(std::vector<float>& curvature, size_t k) const {
+    return run(nullptr, &curvature, k, 0.f);
+  }
+  // radius (:131-177)
+  const NormalEstimation3f& estimateNormalsAndCurvatureRadius(VectorSet3f& normals, std::vector<float>& curvature,
+                                                              float radius) const {
+    return run(&normals, &curvature, 0, radius);
+  }
+  const NormalEstimation3f& estimateNormalsRadius(VectorSet3f& normals, float radius) const {
+    return run(&normals, nullptr, 0, radius);
+  }
+  VectorSet3f estimateNormalsRadius(float radius) const {
+    VectorSet3f n;
+    run(&n, nullptr, 0, radius);
+    return n;
+  }
+  const NormalEstimation3f& estimateCurvatureRadius(std::vector<float>& curvature, float radius) const {
+    return run(nullptr, &curvature, 0, radius);
+  }
+  // kNN in radius (:179-232)
+  const NormalEstimation3f& estimateNormalsAndCurvatureKNNInRadius(VectorSet3f& normals,
+                                                                   std::vector<float>& curvature, size_t k,
+                                                                   float radius) const {
+    return run(&normals, &curvature, k, radius);
+  }
+  const NormalEstimation3f& estimateNormalsKNNInRadius(VectorSet3f& normals, size_t k, float radius) const {
+    return run(&normals, nullptr, k, radius);
+  }
+  VectorSet3f estimateNormalsKNNInRadius(size_t k, float radius) const {
+    VectorSet3f n;
+    run(&n, nullptr, k, radius);
+    return n;
+  }
+  const NormalEstimation3f& estimateCurvatureKNNInRadius(std::vector<float>& curvature, size_t k,
+                                                         float radius) const {
+    return run(nullptr, &curvature, k, radius);
+  }
+
+private:
+  const NormalEstimation3f& run(VectorSet3f* normals, std::vector<float>* curvature, size_t k, float radius) const {
+    if (k > 32) throw std::runtime_error("cilantro_b200: normal estimation supports k <= 32 neighbours");
+    if (normals) normals->resize(3, n_);
+    if (curvature) curvature->resize(n_);
+    if (n_ == 0) return *this;
+    const float nan = std::numeric_limits<float>::quiet_NaN();
+    if (k == 0 && !(radius > 0.f)) {  // empty neighbourhoods: every sample is below the minimum size
+      if (normals) std::fill(normals->data(), normals->data() + 3 * n_, nan);
+      if (curvature) std::fill(curvature->begin(), curvature->end(), nan);
+      return *this;
+    }
+    if (use_ref_) {  // re-upload the reference normals: the previous call overwrote the cloud's normals
+      ConstVectorSetMatrixMap3f ref(ref_normals_);
+      cloud_.reset(points_, &ref);
+    }
+    b200::check(cb_cloud_estimate_normals(b200::Context::get(), cloud_.h, (int)k, radius, view_point_.data(),
+                                          use_ref_ ? 1 : 0, normals ? normals->data() : nullptr,
+                                          curvature ? curvature->data() : nullptr, nullptr, nullptr),
+                "cb_cloud_estimate_normals");
+    return *this;
+  }
+  size_t n_;
+  ConstVectorSetMatrixMap3f points_;
+  mutable b200::CloudHandle cloud_;
+  Vector3f view_point_;
+  std::vector<float> ref_normals_;
+  bool use_ref_ = false;
+};
+
 struct PointCloud3f {
   VectorSet3f points, normals, colors;
+  // utilities/point_cloud.hpp:292-420: view point = origin unless the current normals serve as the
+  // reference (use_current_as_ref && hasNormals())
+  PointCloud3f& estimateNormalsKNN(size_t k, bool use_current_as_ref = false) {
+    normal_estimator(use_current_as_ref).estimateNormalsKNN(normals, k);
+    return *this;
+  }
+  PointCloud3f& estimateNormalsRadius(float radius, bool use_current_as_ref = false) {
+    normal_estimator(use_current_as_ref).estimateNormalsRadius(normals, radius);
+    return *this;
+  }
+  PointCloud3f& estimateNormalsKNNInRadius(size_t k, float radius, bool use_current_as_ref = false) {
+    normal_estimator(use_current_as_ref).estimateNormalsKNNInRadius(normals, k, radius);
+    return *this;
+  }
+  // overloads taking the caller's search tree (utilities/point_cloud.hpp:311-327 etc.): same result
+  template <typename IndexT>
+  PointCloud3f& estimateNormalsKNN(const KDTree3f<IndexT>&, size_t k, bool use_current_as_ref = false) {
+    return estimateNormalsKNN(k, use_current_as_ref);
+  }
+  template <typename IndexT>
+  PointCloud3f& estimateNormalsRadius(const KDTree3f<IndexT>&, float radius, bool use_current_as_ref = false) {
+    return estimateNormalsRadius(radius, use_current_as_ref);
+  }
+  template <typename IndexT>
+  PointCloud3f& estimateNormalsKNNInRadius(const KDTree3f<IndexT>&, size_t k, float radius,
+                                           bool use_current_as_ref = false) {
+    return estimateNormalsKNNInRadius(k, radius, use_current_as_ref);
+  }
+  NormalEstimation3f normal_estimator(bool use_current_as_ref) const {
+    NormalEstimation3f ne(points);
+    if (use_current_as_ref && hasNormals())
+      ne.setReferenceNormals(normals);
+    else
+      ne.setViewPoint(Vector3f(0.f, 0.f, 0.f));
+    return ne;
+  }
   size_t size() const { return points.cols(); }
   bool hasNormals() const { return size() > 0 && normals.cols() == size(); }
   bool hasColors() const { return size() > 0 && colors.cols() == size(); }

@@ -110,6 +110,20 @@ int cb_knn1_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, co
  * idx/d2 are n_qry x k, ascending d2, unused slots idx = -1. counts (may be NULL) = found per query. */
 int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, int k,
                   float max_d2, int64_t* idx, float* d2, uint32_t* counts);
+/* ---- normal / curvature estimation -------------------------------------------------------------
+ * Replaces NormalEstimation::estimateNormalsAndCurvature{KNN,Radius,KNNInRadius} (core/
+ * normal_estimation.hpp:83-232 -> compute_normals_curvature_* :357-421) as called by
+ * PointCloud::estimateNormals* (utilities/point_cloud.hpp:294-420). Neighbourhood of every point over
+ * the cloud itself:  k > 0, radius2 <= 0 : kNN;  k > 0, radius2 > 0 : kNN within squared radius;
+ * k == 0, radius2 > 0 : all points with d2 < radius2 (cilantro radii are squared distances).
+ * Fewer than 3 neighbours -> NaN. view_point3 (may be NULL or non-finite = no orientation step) flips
+ * each normal towards the view point (:325-329); use_current_as_ref != 0 on a cloud that has normals
+ * orients by those instead (setReferenceNormals, :63-69, :351-355; takes precedence, :281-291). The normals are stored in the cloud on the device (as
+ * PointCloud::normals is filled), so a combined-metric ICP can follow without a host round trip.
+ * Host outputs (each may be NULL): normals 3n, curvature n, cov6 6n (xx,xy,xz,yy,yz,zz of the
+ * neighbourhood covariance, diagnostic). gpu_ms (may be NULL) = device time of the kernel. k <= 32. */
+int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k, float radius2, const float* view_point3,
+                              int use_current_as_ref, float* normals, float* curvature, float* cov6, float* gpu_ms);
 /* findNNCorrespondencesUnidirectional(ref_is_first = true), compacted in query order:
  * (index_first[c], index_second[c], value[c]) = (ref idx, query idx, d2). Arrays sized n_qry. */
 int cb_find_correspondences(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12,

@@ -162,6 +162,17 @@ class BruteKnn:
                              C.c_float(max_d2), _p(idx), _p(d2))
         return idx, d2
 
+    def neighborhoods(self, qry, k, r2, stride=None):
+        """k nearest with d2 < r2 (k == 0: all within r2), ascending (d2, index): idx [nq, stride], d2, cnt."""
+        qry = _f32(qry)
+        stride = int(stride or k)
+        idx = np.empty((qry.shape[0], stride), np.int64)
+        d2 = np.empty((qry.shape[0], stride), np.float32)
+        cnt = np.empty(qry.shape[0], np.uint32)
+        lib().orc_neighborhoods_brute(_p(self.pts), C.c_size_t(self.pts.shape[0]), _p(qry), C.c_size_t(qry.shape[0]),
+                                      C.c_size_t(k), C.c_float(r2), C.c_size_t(stride), _p(idx), _p(d2), _p(cnt))
+        return idx, d2, cnt
+
 
 class RefKnn:
     """The reference's own nanoflann kd-tree (leaf 10, 1 build thread), via oracle/_ref."""
@@ -205,6 +216,22 @@ class RefKnn:
         d2 = np.empty(k, np.float32)
         n = ref().ref_knn_in_radius(self.h, _p(q), C.c_size_t(k), C.c_float(r2), _p(idx), _p(d2))
         return idx[:n].astype(np.int64), d2[:n]
+
+    def neighborhoods(self, qry, k, r2, stride=None):
+        """Batched kNNInRadiusSearch (k > 0) or radiusSearch (k == 0): idx [nq, stride], d2, cnt."""
+        qry = _f32(qry)
+        stride = int(stride or k)
+        idx = np.empty((qry.shape[0], stride), np.int64)
+        d2 = np.empty((qry.shape[0], stride), np.float32)
+        cnt = np.empty(qry.shape[0], np.uint32)
+        if k > 0:
+            assert stride == k
+            ref().ref_knn_in_radius_batch(self.h, _p(qry), C.c_size_t(qry.shape[0]), C.c_size_t(k), C.c_float(r2),
+                                          _p(idx), _p(d2), _p(cnt))
+        else:
+            ref().ref_radius_batch(self.h, _p(qry), C.c_size_t(qry.shape[0]), C.c_float(r2), C.c_size_t(stride),
+                                   _p(idx), _p(d2), _p(cnt))
+        return idx, d2, cnt
 
 
 def make_knn(ref_pts, prefer_ref=True):
@@ -386,6 +413,29 @@ def ransac_rigid(dst, src, seed, max_iter=100, thresh=0.01, inlier_count_thresh=
         "inliers": inl[: res.num_inliers].astype(np.int64),
         "residuals": resid,
     }
+
+
+FLT_MAX = float(np.finfo(np.float32).max)
+
+
+def estimate_normals(pts, knn, k=0, radius2=None, view_point=None, ref_normals=None):
+    """NormalEstimation::estimateNormalsAndCurvature{KNN,Radius,KNNInRadius} (core/normal_estimation.hpp:83-232)
+    on neighbourhoods from `knn` (RefKnn = the reference's nanoflann). Returns normals, curvature, cov6, cnt."""
+    pts = _f32(pts)
+    n = pts.shape[0]
+    r2 = FLT_MAX if radius2 is None else float(radius2)
+    if k > 0:
+        idx, _, cnt = knn.neighborhoods(pts, k, r2)
+    else:
+        _, _, cnt = knn.neighborhoods(pts, 0, r2, stride=1)
+        idx, _, cnt = knn.neighborhoods(pts, 0, r2, stride=max(1, int(cnt.max()) if n else 1))
+    normals = np.empty((n, 3), np.float32)
+    curv = np.empty(n, np.float32)
+    cov6 = np.empty((n, 6), np.float32)
+    vp = None if view_point is None else np.ascontiguousarray(view_point, np.float32).reshape(3)
+    lib().orc_normals_from_neighbors(_p(pts), C.c_size_t(n), _p(idx), C.c_size_t(idx.shape[1]), _p(cnt), _p(vp),
+                                     _p(_f32(ref_normals) if ref_normals is not None else None), _p(normals), _p(curv), _p(cov6))
+    return normals, curv, cov6, cnt
 
 
 def pca(pts, accum_double=False):

@@ -939,6 +939,109 @@ ORC_API int orc_pca(const float* pts, size_t n, int accum_double, float* mean3, 
   return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Normal (and curvature) estimation from given neighbourhoods — core/normal_estimation.hpp.
+// The neighbourhood of point i is nbr[i*stride .. i*stride+cnt[i]) in the order the search returned
+// it (ascending distance: KNNSearchResultAdaptor keeps its slots sorted, kd_tree.hpp:77-99; the
+// radius adaptor sorts, kd_tree.hpp:130-133); the tests fill it from the reference's own nanoflann
+// (oracle/_ref). Per point (normal_estimation.hpp:298-308 / :319-332 / curvature :379-389):
+//   * fewer than 3 neighbours (setMinValidSampleSize(points_.rows()), :27/:38; covariance.hpp:93-97)
+//     -> NaN normal and curvature;
+//   * mean_sum += p sequentially, mean = (1/size) * mean_sum; cov_sum += (p-mean)(p-mean)^T
+//     sequentially, cov = (1/(size-1)) * cov_sum — all fp32 (covariance.hpp:121-135), restated
+//     bit-exactly (cov6 = xx,xy,xz,yy,yz,zz);
+//   * normal = eigenvectors().col(0) of SelfAdjointEigenSolver(cov) (ascending eigenvalues): Eigen is
+//     absent from this image, so the eigenvector comes from a double Jacobi (small_linalg.hpp) —
+//     parity UNPINNED for this O(1) step; its sign is an artefact of Eigen's QR iteration unless a
+//     view point is set, in which case it is flipped when dot(n, view_point - p) < 0 (:325-329);
+//   * curvature = eigenvalues()[0] / eigenvalues().sum() (:389).
+ORC_API void orc_normals_from_neighbors(const float* pts, size_t n, const int64_t* nbr, size_t stride,
+                                        const uint32_t* cnt, const float* view_point3,
+                                        const float* ref_normals, float* normals, float* curvature,
+                                        float* cov6) {
+  const float nan = std::numeric_limits<float>::quiet_NaN();
+  const bool use_vp = view_point3 && std::isfinite(view_point3[0]) && std::isfinite(view_point3[1]) &&
+                      std::isfinite(view_point3[2]);  // view_point_.allFinite(), :283
+#pragma omp parallel for schedule(static)
+  for (size_t i = 0; i < n; i++) {
+    const size_t m = cnt[i];
+    const int64_t* nb = nbr + i * stride;
+    if (m < 3) {
+      if (normals) normals[3 * i] = normals[3 * i + 1] = normals[3 * i + 2] = nan;
+      if (curvature) curvature[i] = nan;
+      if (cov6)
+        for (int c = 0; c < 6; c++) cov6[6 * i + c] = nan;
+      continue;
+    }
+    float ms[3] = {0.f, 0.f, 0.f};
+    for (size_t j = 0; j < m; j++)
+      for (int c = 0; c < 3; c++) ms[c] = ms[c] + pts[3 * nb[j] + c];
+    const float inv = 1.0f / (float)m;
+    const float mean[3] = {inv * ms[0], inv * ms[1], inv * ms[2]};
+    float cs[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (size_t j = 0; j < m; j++) {
+      const float dx = pts[3 * nb[j]] - mean[0], dy = pts[3 * nb[j] + 1] - mean[1], dz = pts[3 * nb[j] + 2] - mean[2];
+      cs[0] = cs[0] + dx * dx;
+      cs[1] = cs[1] + dx * dy;
+      cs[2] = cs[2] + dx * dz;
+      cs[3] = cs[3] + dy * dy;
+      cs[4] = cs[4] + dy * dz;
+      cs[5] = cs[5] + dz * dz;
+    }
+    const float invm1 = 1.0f / (float)(m - 1);
+    float cv[6];
+    for (int c = 0; c < 6; c++) cv[c] = invm1 * cs[c];
+    if (cov6)
+      for (int c = 0; c < 6; c++) cov6[6 * i + c] = cv[c];
+    orc::M3 C, V;
+    C.a[0][0] = cv[0]; C.a[0][1] = C.a[1][0] = cv[1]; C.a[0][2] = C.a[2][0] = cv[2];
+    C.a[1][1] = cv[3]; C.a[1][2] = C.a[2][1] = cv[4]; C.a[2][2] = cv[5];
+    double w[3];
+    orc::sym3_eigen(C, w, V);
+    float nv[3] = {(float)V.a[0][0], (float)V.a[1][0], (float)V.a[2][0]};
+    if (ref_normals) {  // reference normals take precedence (:281-291); flip rule :351-355
+      const float* r = ref_normals + 3 * i;
+      const float d = nv[0] * r[0] + (nv[1] * r[1] + nv[2] * r[2]);
+      if (d < 0.f)
+        for (int c = 0; c < 3; c++) nv[c] = -nv[c];
+    } else if (use_vp) {
+      const float ex = view_point3[0] - pts[3 * i], ey = view_point3[1] - pts[3 * i + 1],
+                  ez = view_point3[2] - pts[3 * i + 2];
+      const float d = nv[0] * ex + (nv[1] * ey + nv[2] * ez);
+      if (d < 0.f)
+        for (int c = 0; c < 3; c++) nv[c] = -nv[c];
+    }
+    if (normals)
+      for (int c = 0; c < 3; c++) normals[3 * i + c] = nv[c];
+    if (curvature) curvature[i] = (float)(w[0] / (w[0] + w[1] + w[2]));
+  }
+}
+
+// Brute-force neighbourhoods (stand-in when oracle/_ref is not built): k nearest with d2 < max_d2, or —
+// k == 0 — every point with d2 < max_d2, ascending (d2, index); rows truncated to `stride`, cnt = full
+// count. Distance arithmetic as nanoflann's L2_Adaptor::evalMetric for dim 3: ((dx^2)+dy^2)+dz^2.
+ORC_API void orc_neighborhoods_brute(const float* ref, size_t nr, const float* qry, size_t nq, size_t k,
+                                     float max_d2, size_t stride, int64_t* idx, float* d2, uint32_t* cnt) {
+#pragma omp parallel for schedule(dynamic, 64)
+  for (size_t i = 0; i < nq; i++) {
+    std::vector<std::pair<float, int64_t>> c;
+    const float qx = qry[3 * i], qy = qry[3 * i + 1], qz = qry[3 * i + 2];
+    for (size_t j = 0; j < nr; j++) {
+      const float dx = qx - ref[3 * j], dy = qy - ref[3 * j + 1], dz = qz - ref[3 * j + 2];
+      const float r = ((dx * dx) + dy * dy) + dz * dz;
+      if (r < max_d2) c.emplace_back(r, (int64_t)j);
+    }
+    std::sort(c.begin(), c.end());
+    size_t m = c.size();
+    if (k > 0 && m > k) m = k;
+    for (size_t j = 0; j < stride; j++) {
+      idx[i * stride + j] = j < m ? c[j].second : -1;
+      d2[i * stride + j] = j < m ? c[j].first : max_d2;
+    }
+    cnt[i] = (uint32_t)m;
+  }
+}
+
 ORC_API int orc_num_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

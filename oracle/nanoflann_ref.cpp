@@ -150,4 +150,48 @@ REF_API void ref_nn1(void* h, const float* qry, size_t nq, int64_t* idx, float* 
   }
 }
 
+// Batched kNNInRadiusSearch / kNNSearch (core/kd_tree.hpp:233-240, 302-309): row i of idx/d2 holds
+// the neighbours of query i in ascending distance, cnt[i] of them (unused slots: -1 / r2).
+REF_API void ref_knn_in_radius_batch(void* h, const float* qry, size_t nq, size_t k, float r2, int64_t* idx,
+                                     float* d2, uint32_t* cnt) {
+  RefTree* t = (RefTree*)h;
+  const nanoflann::SearchParameters sp(0.0f, true);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (size_t i = 0; i < nq; i++) {
+    std::vector<float> v(k);
+    std::vector<size_t> ix(k);
+    size_t m = 0;
+    if (t->data.n > 0 && k > 0) {
+      BoundedKBest rs(v.data(), ix.data(), k, r2);
+      t->tree->findNeighbors(rs, qry + 3 * i, sp);
+      m = rs.size();
+    }
+    for (size_t j = 0; j < k; j++) {
+      idx[i * k + j] = j < m ? (int64_t)ix[j] : -1;
+      d2[i * k + j] = j < m ? v[j] : r2;
+    }
+    cnt[i] = (uint32_t)m;
+  }
+}
+
+// Batched radiusSearch (core/kd_tree.hpp:251-272) through nanoflann's own radiusSearch, which
+// collects every point with d2 < r2 and sorts by distance like RadiusSearchResultAdaptor::sort
+// (kd_tree.hpp:130-133). Rows are truncated to `stride` entries; cnt[i] is the full count.
+REF_API void ref_radius_batch(void* h, const float* qry, size_t nq, float r2, size_t stride, int64_t* idx,
+                              float* d2, uint32_t* cnt) {
+  RefTree* t = (RefTree*)h;
+  const nanoflann::SearchParameters sp(0.0f, true);
+#pragma omp parallel for schedule(dynamic, 256)
+  for (size_t i = 0; i < nq; i++) {
+    std::vector<nanoflann::ResultItem<size_t, float>> out;
+    size_t m = 0;
+    if (t->data.n > 0) m = t->tree->radiusSearch(qry + 3 * i, r2, out, sp);
+    for (size_t j = 0; j < stride; j++) {
+      idx[i * stride + j] = j < m ? (int64_t)out[j].first : -1;
+      d2[i * stride + j] = j < m ? out[j].second : r2;
+    }
+    cnt[i] = (uint32_t)m;
+  }
+}
+
 REF_API unsigned ref_nanoflann_version() { return NANOFLANN_VERSION; }

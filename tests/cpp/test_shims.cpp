@@ -89,6 +89,43 @@ int main() {
     src.points.setCol(i, p);
   }
   src.transform(tf_ref);
+  // ---- normal_estimation.cpp: NormalEstimation3f / PointCloud3f::estimateNormalsKNN ------------------------
+  {
+    cilantro::KDTree3f<> tree(dst.points);
+    cilantro::NormalEstimation3f ne(tree);
+    ne.setViewPoint(cilantro::Vector3f(0.f, 0.f, 10.f));
+    cilantro::VectorSet3f est = ne.getNormalsKNN(12);
+    std::vector<float> curv;
+    ne.estimateCurvatureKNNInRadius(curv, 12, 0.05f * 0.05f);
+    CHECK(est.cols() == N && curv.size() == N);
+    double acc = 0;
+    size_t bad = 0;
+    for (size_t i = 0; i < N; i++) {
+      const cilantro::Vector3f a = est.col(i), b = dst.normals.col(i);
+      const float d = a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
+      acc += d;
+      bad += (d < 0.9f);
+      CHECK(std::fabs(a.norm() - 1.f) < 1e-4f);
+      CHECK(std::isnan(curv[i]) || (curv[i] > -1e-5f && curv[i] < 0.34f));
+    }
+    std::printf("normals: mean dot with analytic %.4f, %zu of %zu below 0.9\n", acc / N, bad, N);
+    CHECK(acc / N > 0.98 && bad < N / 50);
+    // PointCloud API: view point = origin; then the current normals as the reference keep their side
+    cilantro::PointCloud3f pc;
+    pc.points = dst.points;
+    pc.normals = dst.normals;
+    pc.estimateNormalsKNN(tree, 12, /*use_current_as_ref=*/true);
+    CHECK(pc.hasNormals());
+    size_t differ = 0;  // same eigenvector; the side may differ only where it is (nearly) tangent to both rules
+    for (size_t i = 0; i < N; i++) {
+      const cilantro::Vector3f a = pc.normals.col(i), b = est.col(i);
+      const bool same = std::fabs(a[0] - b[0]) < 1e-6f && std::fabs(a[1] - b[1]) < 1e-6f && std::fabs(a[2] - b[2]) < 1e-6f;
+      const bool flipped = std::fabs(a[0] + b[0]) < 1e-6f && std::fabs(a[1] + b[1]) < 1e-6f && std::fabs(a[2] + b[2]) < 1e-6f;
+      CHECK(same || flipped);
+      differ += flipped;
+    }
+    CHECK(differ < N / 100);
+  }
   {
     cilantro::Timer timer;
     timer.start();
