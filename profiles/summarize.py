@@ -115,6 +115,8 @@ def main():
          "500 k correspondences x 256 hypotheses per launch, inlier counts only.", None),
         (f"prof_{rnd}_moments.ncu-rep", f"{rnd}_moments_kernel.md", "moments_kernel — bench.py pca_50m",
          "50 M points, one streaming pass (mean + covariance moments in double).", None),
+        (f"normals_knn_{rnd}.ncu-rep", f"{rnd}_normals_knn_kernel.md", "normals_knn_kernel<16> — bench.py normals_1m",
+         "1 M-point noisy sheet, k = 10: k-best grid search + neighbourhood covariance + 3x3 Jacobi eigen-solve per point.", None),
     ]
     traffic = {}
     tpath = os.path.join(HERE, "traffic.json")
