@@ -72,7 +72,7 @@ EXPORTED = [
     "cb_context_kernel_launches", "cb_context_flush_l2",
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
-    "cb_cloud_estimate_normals",
+    "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
     "cb_knn1_radius", "cb_knn_radius", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
     "cb_icp_correspondences", "cb_icp_residuals", "cb_icp_accumulate",
@@ -239,12 +239,54 @@ class Cloud:
                                                C.c_int(int(use_current_as_ref)), _p(nrm), _p(curv), _p(cov), C.byref(ms)))
         return {"normals": nrm, "curvature": curv, "cov6": cov, "gpu_ms": ms.value}
 
+    @classmethod
+    def _wrap(cls, ctx, handle):
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        self.h = handle
+        self.n = int(lib().cb_cloud_size(handle))
+        ctx._adopt(self)
+        return self
+
+    def grid_downsample(self, bin_size, min_points=1, order=0):
+        """cb_cloud_grid_downsample: a new device-resident Cloud (points + normals if present); .gpu_ms = device time."""
+        h = C.c_void_p()
+        ms = C.c_float()
+        _check(lib().cb_cloud_grid_downsample(self.ctx.h, self.h, C.c_float(bin_size), C.c_size_t(min_points),
+                                              C.c_int(order), C.byref(h), C.byref(ms)))
+        out = Cloud._wrap(self.ctx, h)
+        out.gpu_ms = ms.value
+        return out
+
+    def download(self, normals=False):
+        xyz = np.empty((self.n, 3), np.float32)
+        nrm = np.empty((self.n, 3), np.float32) if normals else None
+        _check(lib().cb_cloud_download(self.ctx.h, self.h, _p(xyz), _p(nrm)))
+        return (xyz, nrm) if normals else xyz
+
     def grid_info(self):
         edge = C.c_float()
         dims = (C.c_int * 3)()
         occ = C.c_double()
         _check(lib().cb_cloud_grid_info(self.h, C.byref(edge), dims, C.byref(occ)))
         return {"cell_edge": edge.value, "dims": list(dims), "mean_occupancy": occ.value}
+
+
+def grid_downsample(ctx, xyz, bin_size, normals=None, colors=None, min_points=1, order=0):
+    """cb_grid_downsample on host arrays: returns (points, normals or None, colors or None)."""
+    xyz = _f32(xyz)
+    n = xyz.shape[0]
+    nrm = _f32(normals) if normals is not None else None
+    col = _f32(colors) if colors is not None else None
+    o_xyz = np.empty((n, 3), np.float32)
+    o_nrm = np.empty((n, 3), np.float32) if nrm is not None else None
+    o_col = np.empty((n, 3), np.float32) if col is not None else None
+    m = C.c_size_t()
+    _check(lib().cb_grid_downsample(ctx.h, _p(xyz), _p(nrm), _p(col), C.c_size_t(n), C.c_float(bin_size),
+                                    C.c_size_t(min_points), C.c_int(order), _p(o_xyz), _p(o_nrm), _p(o_col),
+                                    C.byref(m)))
+    m = m.value
+    return o_xyz[:m].copy(), (o_nrm[:m].copy() if o_nrm is not None else None), (o_col[:m].copy() if o_col is not None else None)
 
 
 def knn1_radius(ctx, ref, qry, T=None, max_d2=np.finfo(np.float32).max):

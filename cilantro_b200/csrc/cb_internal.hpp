@@ -139,6 +139,14 @@ struct cb_cloud {
 namespace cb {
 
 int ensure_index(cb_cloud* c);
+// Finite-coordinate bounding box of n packed xyz points in device memory (synchronises the stream).
+int points_bbox(cb_context* ctx, const float* d_raw, size_t n, float mn[3], float mx[3]);
+// d_data has n + 1 entries; on return d_data[i] = sum_{j<i} in[j], d_data[n] = total (grid_index.cu).
+int exclusive_scan_u32(cb_context* ctx, uint32_t* d_data, size_t n, uint32_t total);
+// Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the keys (radix_sort.cu). The
+// result is left in d_keys / d_vals; d_keys_tmp / d_vals_tmp are same-sized scratch.
+int radix_sort_pairs_u64(cb_context* ctx, uint64_t* d_keys, uint32_t* d_vals, uint64_t* d_keys_tmp,
+                         uint32_t* d_vals_tmp, size_t n, int bits);
 GridView grid_view(const cb_cloud* c);
 // Scratch for a grid_reduce over `blocks` blocks of `nv` values each (grown on demand).
 int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out);

@@ -293,6 +293,24 @@ int exclusive_scan_u32(cb_context* ctx, uint32_t* d_data, size_t n, uint32_t tot
   return CB_OK;
 }
 
+int points_bbox(cb_context* ctx, const float* d_raw, size_t n, float mn[3], float mx[3]) {
+  int* d_bb = nullptr;
+  CB_CUDA(cudaMallocAsync(&d_bb, 6 * sizeof(int), ctx->stream));
+  bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(d_bb);
+  bbox_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(d_raw, n, d_bb);
+  ctx->launches += 2;
+  int h_bb[6];
+  CB_CUDA(cudaMemcpyAsync(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  CB_CUDA(cudaFreeAsync(d_bb, ctx->stream));
+  for (int a = 0; a < 3; a++) {
+    mn[a] = ordered_to_float(h_bb[a]);
+    mx[a] = ordered_to_float(h_bb[3 + a]);
+    if (!(mn[a] <= mx[a])) mn[a] = mx[a] = 0.f;  // no finite coordinate on this axis
+  }
+  return CB_OK;
+}
+
 int ensure_index(cb_cloud* c) {
   if (c->indexed) return CB_OK;
   cb_context* ctx = c->ctx;
@@ -308,21 +326,8 @@ int ensure_index(cb_cloud* c) {
     return CB_OK;
   }
   // 1. bounding box
-  int* d_bb = nullptr;
-  CB_CUDA(cudaMallocAsync(&d_bb, 6 * sizeof(int), ctx->stream));
-  bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(d_bb);
-  bbox_kernel<<<grid_blocks(ctx, n), kThreads, 0, ctx->stream>>>(c->d_raw, n, d_bb);
-  ctx->launches += 2;
-  int h_bb[6];
-  CB_CUDA(cudaMemcpyAsync(h_bb, d_bb, sizeof(h_bb), cudaMemcpyDeviceToHost, ctx->stream));
-  CB_CUDA(cudaStreamSynchronize(ctx->stream));
-  CB_CUDA(cudaFreeAsync(d_bb, ctx->stream));
   float mn[3], mx[3];
-  for (int a = 0; a < 3; a++) {
-    mn[a] = ordered_to_float(h_bb[a]);
-    mx[a] = ordered_to_float(h_bb[3 + a]);
-    if (!(mn[a] <= mx[a])) mn[a] = mx[a] = 0.f;  // no finite coordinate on this axis
-  }
+  CB_TRY(points_bbox(ctx, c->d_raw, n, mn, mx));
   double ext[3] = {(double)mx[0] - mn[0], (double)mx[1] - mn[1], (double)mx[2] - mn[2]};
   const double max_ext = std::max({ext[0], ext[1], ext[2], 1e-30});
 

@@ -725,8 +725,153 @@ private:
   bool use_ref_ = false;
 };
 
+// ---- voxel-grid downsampling (core/grid_downsampler.hpp, core/grid_accumulator.hpp) ---------------------
+// One implementation behind the four reference class names: the constructor takes the same arguments
+// (points [, normals] [, colors], bin_size, parallel); parallel selects the reference's output order
+// (true: bins in lexicographic (x, y, z) order, the std::map order of the parallel build; false: in order
+// of first occurrence, the serial build). The per-bin sums are always the serial build's (index order).
+namespace b200 {
+class GridDownsampler {
+public:
+  GridDownsampler(const ConstVectorSetMatrixMap3f& points, const ConstVectorSetMatrixMap3f* normals,
+                  const ConstVectorSetMatrixMap3f* colors, float bin_size, bool parallel)
+      : points_(points), normals_(normals ? *normals : ConstVectorSetMatrixMap3f()),
+        colors_(colors ? *colors : ConstVectorSetMatrixMap3f()), has_n_(normals != nullptr), has_c_(colors != nullptr),
+        bin_size_(bin_size), order_(parallel ? 0 : 1) {}
+
+protected:
+  void run(VectorSet3f* ds_points, VectorSet3f* ds_normals, VectorSet3f* ds_colors, size_t min_points_in_bin) const {
+    const size_t n = points_.cols();
+    VectorSet3f p(3, n), nn(3, has_n_ ? n : 0), cc(3, has_c_ ? n : 0);
+    size_t m = 0;
+    check(cb_grid_downsample(Context::get(), points_.data(), has_n_ ? normals_.data() : nullptr,
+                             has_c_ ? colors_.data() : nullptr, n, bin_size_, min_points_in_bin, order_, p.data(),
+                             has_n_ ? nn.data() : nullptr, has_c_ ? cc.data() : nullptr, &m),
+          "cb_grid_downsample");
+    p.resize(3, m);
+    if (ds_points) *ds_points = std::move(p);
+    if (ds_normals && has_n_) {
+      nn.resize(3, m);
+      *ds_normals = std::move(nn);
+    }
+    if (ds_colors && has_c_) {
+      cc.resize(3, m);
+      *ds_colors = std::move(cc);
+    }
+  }
+  ConstVectorSetMatrixMap3f points_, normals_, colors_;
+  bool has_n_, has_c_;
+  float bin_size_;
+  int order_;
+};
+}  // namespace b200
+
+class PointsGridDownsampler3f : public b200::GridDownsampler {  // grid_downsampler.hpp:8-44
+public:
+  PointsGridDownsampler3f(const ConstVectorSetMatrixMap3f& points, float bin_size, bool parallel = true)
+      : GridDownsampler(points, nullptr, nullptr, bin_size, parallel) {}
+  const PointsGridDownsampler3f& getDownsampledPoints(VectorSet3f& ds_points, size_t min_points_in_bin = 1) const {
+    run(&ds_points, nullptr, nullptr, min_points_in_bin);
+    return *this;
+  }
+  VectorSet3f getDownsampledPoints(size_t min_points_in_bin = 1) const {
+    VectorSet3f p;
+    run(&p, nullptr, nullptr, min_points_in_bin);
+    return p;
+  }
+};
+
+class PointsNormalsGridDownsampler3f : public b200::GridDownsampler {  // grid_downsampler.hpp:46-132
+public:
+  PointsNormalsGridDownsampler3f(const ConstVectorSetMatrixMap3f& points, const ConstVectorSetMatrixMap3f& normals,
+                                 float bin_size, bool parallel = true)
+      : GridDownsampler(points, &normals, nullptr, bin_size, parallel) {}
+  const PointsNormalsGridDownsampler3f& getDownsampledPoints(VectorSet3f& p, size_t min_points_in_bin = 1) const {
+    run(&p, nullptr, nullptr, min_points_in_bin);
+    return *this;
+  }
+  const PointsNormalsGridDownsampler3f& getDownsampledNormals(VectorSet3f& nn, size_t min_points_in_bin = 1) const {
+    run(nullptr, &nn, nullptr, min_points_in_bin);
+    return *this;
+  }
+  const PointsNormalsGridDownsampler3f& getDownsampledPointsNormals(VectorSet3f& p, VectorSet3f& nn,
+                                                                    size_t min_points_in_bin = 1) const {
+    run(&p, &nn, nullptr, min_points_in_bin);
+    return *this;
+  }
+};
+
+class PointsColorsGridDownsampler3f : public b200::GridDownsampler {  // grid_downsampler.hpp:134-220
+public:
+  PointsColorsGridDownsampler3f(const ConstVectorSetMatrixMap3f& points, const ConstVectorSetMatrixMap3f& colors,
+                                float bin_size, bool parallel = true)
+      : GridDownsampler(points, nullptr, &colors, bin_size, parallel) {}
+  const PointsColorsGridDownsampler3f& getDownsampledPoints(VectorSet3f& p, size_t min_points_in_bin = 1) const {
+    run(&p, nullptr, nullptr, min_points_in_bin);
+    return *this;
+  }
+  const PointsColorsGridDownsampler3f& getDownsampledColors(VectorSet3f& cc, size_t min_points_in_bin = 1) const {
+    run(nullptr, nullptr, &cc, min_points_in_bin);
+    return *this;
+  }
+  const PointsColorsGridDownsampler3f& getDownsampledPointsColors(VectorSet3f& p, VectorSet3f& cc,
+                                                                  size_t min_points_in_bin = 1) const {
+    run(&p, nullptr, &cc, min_points_in_bin);
+    return *this;
+  }
+};
+
+class PointsNormalsColorsGridDownsampler3f : public b200::GridDownsampler {  // grid_downsampler.hpp:222-340
+public:
+  PointsNormalsColorsGridDownsampler3f(const ConstVectorSetMatrixMap3f& points,
+                                       const ConstVectorSetMatrixMap3f& normals,
+                                       const ConstVectorSetMatrixMap3f& colors, float bin_size, bool parallel = true)
+      : GridDownsampler(points, &normals, &colors, bin_size, parallel) {}
+  const PointsNormalsColorsGridDownsampler3f& getDownsampledPoints(VectorSet3f& p, size_t min_points_in_bin = 1) const {
+    run(&p, nullptr, nullptr, min_points_in_bin);
+    return *this;
+  }
+  const PointsNormalsColorsGridDownsampler3f& getDownsampledNormals(VectorSet3f& nn,
+                                                                    size_t min_points_in_bin = 1) const {
+    run(nullptr, &nn, nullptr, min_points_in_bin);
+    return *this;
+  }
+  const PointsNormalsColorsGridDownsampler3f& getDownsampledColors(VectorSet3f& cc, size_t min_points_in_bin = 1) const {
+    run(nullptr, nullptr, &cc, min_points_in_bin);
+    return *this;
+  }
+  const PointsNormalsColorsGridDownsampler3f& getDownsampledPointsNormalsColors(VectorSet3f& p, VectorSet3f& nn,
+                                                                                VectorSet3f& cc,
+                                                                                size_t min_points_in_bin = 1) const {
+    run(&p, &nn, &cc, min_points_in_bin);
+    return *this;
+  }
+};
+
 struct PointCloud3f {
   VectorSet3f points, normals, colors;
+  // utilities/point_cloud.hpp:246-290
+  PointCloud3f& gridDownsample(float bin_size, size_t min_points_in_bin = 1, bool parallel = true) {
+    PointCloud3f res = gridDownsampled(bin_size, min_points_in_bin, parallel);
+    *this = std::move(res);
+    return *this;
+  }
+  PointCloud3f gridDownsampled(float bin_size, size_t min_points_in_bin = 1, bool parallel = true) const {
+    PointCloud3f res;
+    if (hasNormals() && hasColors()) {
+      PointsNormalsColorsGridDownsampler3f(points, normals, colors, bin_size, parallel)
+          .getDownsampledPointsNormalsColors(res.points, res.normals, res.colors, min_points_in_bin);
+    } else if (hasNormals()) {
+      PointsNormalsGridDownsampler3f(points, normals, bin_size, parallel)
+          .getDownsampledPointsNormals(res.points, res.normals, min_points_in_bin);
+    } else if (hasColors()) {
+      PointsColorsGridDownsampler3f(points, colors, bin_size, parallel)
+          .getDownsampledPointsColors(res.points, res.colors, min_points_in_bin);
+    } else {
+      PointsGridDownsampler3f(points, bin_size, parallel).getDownsampledPoints(res.points, min_points_in_bin);
+    }
+    return res;
+  }
   // utilities/point_cloud.hpp:292-420: view point = origin unless the current normals serve as the
   // reference (use_current_as_ref && hasNormals())
   PointCloud3f& estimateNormalsKNN(size_t k, bool use_current_as_ref = false) {

@@ -124,6 +124,29 @@ int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, con
  * neighbourhood covariance, diagnostic). gpu_ms (may be NULL) = device time of the kernel. k <= 32. */
 int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k, float radius2, const float* view_point3,
                               int use_current_as_ref, float* normals, float* curvature, float* cov6, float* gpu_ms);
+/* ---- voxel-grid downsampling -------------------------------------------------------------------
+ * Replaces PointCloud::gridDownsample / gridDownsampled (utilities/point_cloud.hpp:246-290) =
+ * Points[Normals][Colors]GridDownsampler (core/grid_downsampler.hpp) over GridAccumulator::build_index_
+ * (core/grid_accumulator.hpp:146-199): bin = floor(p * (1 / bin_size)) per axis; per bin the point sum,
+ * the sign-consistent normal sum (core/common_accumulators.hpp:122-131) and the colour sum are taken
+ * in point-index order in fp32 (the serial build's arithmetic, bit for bit) and divided by the count;
+ * normals are re-normalised; bins with fewer than min_points_in_bin points are dropped.
+ * order = 0: bins ascending lexicographically in (x, y, z) — the std::map order the default
+ *            (parallel = true) build emits (:177-181);
+ * order = 1: bins in order of their first point — the serial (parallel = false) build (:194-197).
+ * normals / colors (packed 3 floats per point) may be NULL; outputs are sized for n points, *out_n is
+ * the number of occupied bins written. */
+int cb_grid_downsample(cb_context* ctx, const float* xyz, const float* normals, const float* colors, size_t n,
+                       float bin_size, size_t min_points_in_bin, int order, float* out_xyz, float* out_normals,
+                       float* out_colors, size_t* out_n);
+/* Same on a device-resident cloud (points + normals if it has them); the result is a new cloud that never
+ * leaves HBM (downsample -> cb_cloud_estimate_normals -> cb_icp_* without host round trips). gpu_ms may be
+ * NULL. */
+int cb_cloud_grid_downsample(cb_context* ctx, const cb_cloud* cloud, float bin_size, size_t min_points_in_bin,
+                             int order, cb_cloud** out, float* gpu_ms);
+/* Copies a cloud's points (and normals, if normals != NULL and the cloud has them) back to the host in
+ * original order. */
+int cb_cloud_download(cb_context* ctx, const cb_cloud* cloud, float* xyz, float* normals);
 /* findNNCorrespondencesUnidirectional(ref_is_first = true), compacted in query order:
  * (index_first[c], index_second[c], value[c]) = (ref idx, query idx, d2). Arrays sized n_qry. */
 int cb_find_correspondences(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12,

@@ -438,6 +438,21 @@ def estimate_normals(pts, knn, k=0, radius2=None, view_point=None, ref_normals=N
     return normals, curv, cov6, cnt
 
 
+def grid_downsample(pts, bin_size, normals=None, colors=None, min_points=1, order=0):
+    """PointCloud::gridDownsample (serial sums; order 0 = map order, 1 = first occurrence): points, normals, colors."""
+    pts = _f32(pts)
+    n = pts.shape[0]
+    nrm = _f32(normals) if normals is not None else None
+    col = _f32(colors) if colors is not None else None
+    o_p = np.empty((max(n, 1), 3), np.float32)
+    o_n = np.empty((max(n, 1), 3), np.float32) if nrm is not None else None
+    o_c = np.empty((max(n, 1), 3), np.float32) if col is not None else None
+    lib().orc_grid_downsample.restype = C.c_size_t
+    m = lib().orc_grid_downsample(_p(pts), _p(nrm), _p(col), C.c_size_t(n), C.c_float(bin_size), C.c_size_t(min_points),
+                                  C.c_int(order), _p(o_p), _p(o_n), _p(o_c))
+    return o_p[:m].copy(), (o_n[:m].copy() if o_n is not None else None), (o_c[:m].copy() if o_c is not None else None)
+
+
 def pca(pts, accum_double=False):
     pts = _f32(pts)
     mean = np.empty(3, np.float32)

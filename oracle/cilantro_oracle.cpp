@@ -32,6 +32,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <vector>
 #include <random>
 #include <algorithm>
@@ -1040,6 +1041,155 @@ ORC_API void orc_neighborhoods_brute(const float* ref, size_t nr, const float* q
     }
     cnt[i] = (uint32_t)m;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Voxel-grid downsampling — PointCloud::gridDownsample (utilities/point_cloud.hpp:246-290) over
+// Points[Normals][Colors]GridDownsampler (core/grid_downsampler.hpp) and the SERIAL
+// GridAccumulator::build_index_ (core/grid_accumulator.hpp:187-199):
+//   * grid coordinate = (ptrdiff_t) std::floor(point[i] * bin_size_inv[i]), bin_size_inv = 1/bin_size
+//     in fp32 (:117-126, :87);
+//   * std::map keyed by the coordinate triple, lexicographic with x most significant (:9-39);
+//   * the first point of a bin builds the accumulator (copy), later points are added in index order:
+//     pointSum += p; normalSum +-= n depending on sign(normalSum . n) (common_accumulators.hpp:
+//     122-131); colorSum += c;
+//   * output per bin with pointCount >= min_points: scale = 1.0f / pointCount, scale * pointSum,
+//     (scale * normalSum).normalized(), scale * colorSum (grid_downsampler.hpp:20-37, :97-105).
+// order = 0: bins in map order (what the default parallel = true build emits, :177-181 — its SUMS are
+// merged across threads in arrival order and are not reproducible; the serial sums are restated);
+// order = 1: bins in first-occurrence order (parallel = false, :194-197). Returns the bin count.
+ORC_API size_t orc_grid_downsample(const float* pts, const float* nrm, const float* col, size_t n, float bin_size,
+                                   size_t min_points, int order, float* out_pts, float* out_nrm, float* out_col) {
+  struct Key {
+    std::ptrdiff_t c[3];
+    bool operator<(const Key& o) const {
+      if (c[0] < o.c[0]) return true;
+      if (o.c[0] < c[0]) return false;
+      if (c[1] < o.c[1]) return true;
+      if (o.c[1] < c[1]) return false;
+      return c[2] < o.c[2];
+    }
+  };
+  struct Acc {
+    float p[3], nv[3], cl[3];
+    size_t count;
+  };
+  const float inv = 1.0f / bin_size;
+  std::map<Key, Acc> table;
+  std::vector<std::map<Key, Acc>::iterator> seq;
+#ifdef _OPENMP
+  if (order == 2) {
+    // order = 2: the reference's DEFAULT parallel build (grid_accumulator.hpp:149-181) — per-thread
+    // private maps over a static partition of the points, merged under a critical section in thread
+    // arrival order (mergeWith, common_accumulators.hpp:48-52, :93-103). Same bins and map order as
+    // order 0; the sums differ from the serial ones in the last bits and from run to run. Used as the
+    // CPU baseline of bench.py and for a tolerance test only.
+#pragma omp parallel
+    {
+      std::map<Key, Acc> priv;
+#pragma omp for nowait
+      for (size_t i = 0; i < n; i++) {
+        Key k;
+        for (int a = 0; a < 3; a++) k.c[a] = (std::ptrdiff_t)std::floor(pts[3 * i + a] * inv);
+        auto lb = priv.lower_bound(k);
+        if (lb != priv.end() && !(k < lb->first)) {
+          Acc& acc = lb->second;
+          for (int a = 0; a < 3; a++) acc.p[a] = acc.p[a] + pts[3 * i + a];
+          if (nrm) {
+            const float* v = nrm + 3 * i;
+            const float d = sum3(acc.nv[0] * v[0], acc.nv[1] * v[1], acc.nv[2] * v[2]);
+            for (int a = 0; a < 3; a++) acc.nv[a] = d < 0.f ? acc.nv[a] - v[a] : acc.nv[a] + v[a];
+          }
+          if (col)
+            for (int a = 0; a < 3; a++) acc.cl[a] = acc.cl[a] + col[3 * i + a];
+          acc.count++;
+        } else {
+          Acc acc;
+          for (int a = 0; a < 3; a++) {
+            acc.p[a] = pts[3 * i + a];
+            acc.nv[a] = nrm ? nrm[3 * i + a] : 0.f;
+            acc.cl[a] = col ? col[3 * i + a] : 0.f;
+          }
+          acc.count = 1;
+          priv.emplace_hint(lb, k, acc);
+        }
+      }
+#pragma omp critical
+      {
+        for (auto it = priv.begin(); it != priv.end(); ++it) {
+          auto lb = table.lower_bound(it->first);
+          if (lb != table.end() && !(it->first < lb->first)) {
+            Acc& acc = lb->second;
+            const Acc& o = it->second;
+            for (int a = 0; a < 3; a++) acc.p[a] = acc.p[a] + o.p[a];
+            const float d = sum3(acc.nv[0] * o.nv[0], acc.nv[1] * o.nv[1], acc.nv[2] * o.nv[2]);
+            for (int a = 0; a < 3; a++) acc.nv[a] = d < 0.f ? acc.nv[a] - o.nv[a] : acc.nv[a] + o.nv[a];
+            for (int a = 0; a < 3; a++) acc.cl[a] = acc.cl[a] + o.cl[a];
+            acc.count += o.count;
+          } else {
+            table.emplace_hint(lb, it->first, it->second);
+          }
+        }
+      }
+    }
+    order = 0;
+    n = 0;  // skip the serial build below
+  }
+#endif
+  for (size_t i = 0; i < n; i++) {
+    Key k;
+    for (int a = 0; a < 3; a++) k.c[a] = (std::ptrdiff_t)std::floor(pts[3 * i + a] * inv);
+    auto it = table.find(k);
+    if (it == table.end()) {
+      Acc acc;
+      for (int a = 0; a < 3; a++) {
+        acc.p[a] = pts[3 * i + a];
+        acc.nv[a] = nrm ? nrm[3 * i + a] : 0.f;
+        acc.cl[a] = col ? col[3 * i + a] : 0.f;
+      }
+      acc.count = 1;
+      seq.push_back(table.emplace(k, acc).first);
+    } else {
+      Acc& acc = it->second;
+      for (int a = 0; a < 3; a++) acc.p[a] = acc.p[a] + pts[3 * i + a];
+      if (nrm) {
+        const float* v = nrm + 3 * i;
+        const float d = sum3(acc.nv[0] * v[0], acc.nv[1] * v[1], acc.nv[2] * v[2]);
+        if (d < 0.f)
+          for (int a = 0; a < 3; a++) acc.nv[a] = acc.nv[a] - v[a];
+        else
+          for (int a = 0; a < 3; a++) acc.nv[a] = acc.nv[a] + v[a];
+      }
+      if (col)
+        for (int a = 0; a < 3; a++) acc.cl[a] = acc.cl[a] + col[3 * i + a];
+      acc.count++;
+    }
+  }
+  std::vector<const Acc*> bins;
+  if (order == 0)
+    for (auto it = table.begin(); it != table.end(); ++it) bins.push_back(&it->second);
+  else
+    for (auto& it : seq) bins.push_back(&it->second);
+  size_t m = 0;
+  for (const Acc* b : bins) {
+    if (b->count < min_points) continue;
+    const float scale = 1.0f / (float)b->count;
+    for (int a = 0; a < 3; a++) out_pts[3 * m + a] = scale * b->p[a];
+    if (nrm && out_nrm) {
+      const float w[3] = {scale * b->nv[0], scale * b->nv[1], scale * b->nv[2]};
+      const float z = sum3(w[0] * w[0], w[1] * w[1], w[2] * w[2]);
+      if (z > 0.f) {
+        const float nn = std::sqrt(z);
+        for (int a = 0; a < 3; a++) out_nrm[3 * m + a] = w[a] / nn;
+      } else {
+        for (int a = 0; a < 3; a++) out_nrm[3 * m + a] = w[a];
+      }
+    }
+    if (col && out_col)
+      for (int a = 0; a < 3; a++) out_col[3 * m + a] = scale * b->cl[a];
+    m++;
+  }
+  return m;
 }
 
 ORC_API int orc_num_threads() {

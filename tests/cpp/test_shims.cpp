@@ -7,7 +7,9 @@
 //   examples/ransac_transform_estimator.cpp:79-86  -> RigidTransformRANSACEstimator3f<>
 // Exit code 0 = all checks passed. Built and run by tests/test_cpp_shims.py.
 #include <cilantro/clustering/kmeans.hpp>
+#include <cilantro/core/grid_downsampler.hpp>
 #include <cilantro/core/kd_tree.hpp>
+#include <cilantro/core/normal_estimation.hpp>
 #include <cilantro/core/principal_component_analysis.hpp>
 #include <cilantro/model_estimation/ransac_transform_estimator.hpp>
 #include <cilantro/registration/icp_common_instances.hpp>
@@ -125,6 +127,25 @@ int main() {
       differ += flipped;
     }
     CHECK(differ < N / 100);
+    // gridDownsample (the first step of examples/normal_estimation.cpp): fewer points, unit normals, and the
+    // serial build's order (parallel = false) holds the same bins as the map order
+    cilantro::PointCloud3f ds = pc.gridDownsampled(0.05f);
+    cilantro::PointCloud3f ds_serial = pc.gridDownsampled(0.05f, 1, false);
+    std::printf("gridDownsample(0.05): %zu -> %zu points\n", pc.size(), ds.size());
+    CHECK(ds.size() > 100 && ds.size() < N / 4 && ds.hasNormals() && !ds.hasColors());
+    CHECK(ds_serial.size() == ds.size());
+    double sx = 0, sx2 = 0;
+    for (size_t i = 0; i < ds.size(); i++) {
+      CHECK(std::fabs(ds.normals.col(i).norm() - 1.f) < 1e-5f);
+      sx += ds.points(0, i);
+      sx2 += ds_serial.points(0, i);
+      if (i > 0) CHECK(std::floor(ds.points(0, i) * 20.f) >= std::floor(ds.points(0, i - 1) * 20.f) - 1.f);
+    }
+    CHECK(std::fabs(sx - sx2) < 1e-2);
+    cilantro::VectorSet3f only_pts = cilantro::PointsGridDownsampler3f(pc.points, 0.05f).getDownsampledPoints(3);
+    CHECK(only_pts.cols() > 0 && only_pts.cols() <= ds.size());
+    pc.gridDownsample(0.05f);
+    CHECK(pc.size() == ds.size());
   }
   {
     cilantro::Timer timer;
