@@ -103,8 +103,38 @@ def launches(csv_path):
     return "\n".join(out)
 
 
+def downsample_launches(csv_path, out_path, rnd):
+    """One cb_cloud_grid_downsample call (the last one of the run): time and DRAM bytes per kernel."""
+    rows = list(csv.DictReader([l for l in open(csv_path) if not l.startswith("==")]))
+    start = max(int(r["ID"]) for r in rows if "bin_key_kernel" in r["Kernel Name"])
+    agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+    for r in rows:
+        if int(r["ID"]) < start:
+            continue
+        k = r["Kernel Name"].split("(")[0].split("::")[-1]
+        v = float(r["Metric Value"].replace(",", ""))
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            agg[k][0] += 1
+            agg[k][1] += v / 1e3
+        else:
+            agg[k][2] += v * UNIT.get(r["Metric Unit"], 1.0)
+    tot = sum(v[1] for v in agg.values())
+    lines = [f"# Launches of one `cb_cloud_grid_downsample` call ({rnd}) — bench.py downsample_10m", "",
+             "10 M uniform points, bin 0.01 -> 999 951 bins. `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+             "dram__bytes_write.sum --clock-control none` (serialised, cold cache: compare shares).", "",
+             "| kernel | launches | us | share | DRAM MB |", "|---|---:|---:|---:|---:|"]
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        lines.append(f"| `{k}` | {v[0]} | {v[1]:.1f} | {100 * v[1] / tot:.1f}% | {v[2] / 1e6:.1f} |")
+    lines.append(f"| total | {sum(v[0] for v in agg.values())} | {tot:.1f} | 100% | {sum(v[2] for v in agg.values()) / 1e6:.1f} |")
+    open(out_path, "w").write("\n".join(lines) + "\n")
+
+
 def main():
     rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    dl = os.path.join(OUT, f"launches_downsample_{rnd}.csv")
+    if os.path.exists(dl):
+        downsample_launches(dl, os.path.join(HERE, f"{rnd}_downsample_launches.md"), rnd)
+        print("wrote downsample launches")
     jobs = [
         (f"prof_{rnd}f.ncu-rep", f"{rnd}_icp_pass_kernel.md", "icp_pass_kernel<p2p, search> — bench.py icp_p2p_1m",
          "1 M -> 1 M point-to-point ICP iteration (fused transform + warp-pooled grid 1-NN + Kabsch moments), L2 flushed before the launch.",
