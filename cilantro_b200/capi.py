@@ -34,7 +34,15 @@ class IcpParams(C.Structure):
         ("T_init", C.c_float * 12),
         ("flush_l2", C.c_int32),
         ("timing", C.c_int32),
+        ("search_dir", C.c_int32),
+        ("require_reciprocal", C.c_int32),
+        ("one_to_one", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("inlier_fraction", C.c_double),
     ]
+
+
+SEARCH_DIR = {"second_to_first": 0, "first_to_second": 1, "both": 2}
 
 
 class IcpResult(C.Structure):
@@ -326,7 +334,8 @@ def transform_points(ctx, T, xyz):
 
 
 def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5,
-               T_init=None, flush_l2=False, timing=1):
+               T_init=None, flush_l2=False, timing=1, search_dir="second_to_first", inlier_fraction=1.0,
+               require_reciprocal=False, one_to_one=False):
     p = IcpParams()
     lib().cb_icp_default_params(C.byref(p))
     p.metric = 0 if metric == "p2p" else 1
@@ -341,6 +350,10 @@ def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=
         p.T_init[i] = float(v)
     p.flush_l2 = int(flush_l2)
     p.timing = int(timing)
+    p.search_dir = SEARCH_DIR[search_dir] if isinstance(search_dir, str) else int(search_dir)
+    p.inlier_fraction = float(inlier_fraction)
+    p.require_reciprocal = int(require_reciprocal)
+    p.one_to_one = int(one_to_one)
     return p
 
 
@@ -390,7 +403,7 @@ class Icp:
         return sums[:nv]
 
     def correspondences(self):
-        n = self.src.n
+        n = self.src.n + self.dst.n
         i1 = np.empty(n, np.uint64)
         i2 = np.empty(n, np.uint64)
         v = np.empty(n, np.float32)

@@ -157,6 +157,8 @@ struct cb_icp {
   bool nn_stored = false;   // d_nn_pos / d_nn_d2 hold that search's per-query result
   float T_search[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   float max_d2_search = 0.f;
+  cb::EnginePairs pairs;    // correspondence list of the last iteration in a non-default engine mode
+  bool engine_last = false; // the last estimate() went through icp_engine.cu
   double search_ms = 0;  // CUDA-event time of the fused search+accumulate kernels of the last estimate()
   std::vector<cudaEvent_t> events;
   std::vector<double> iter_ms;
@@ -491,6 +493,8 @@ void cb_icp_default_params(cb_icp_params* p) {
   p->max_opt_iter = 1;               // :44
   p->opt_tol = 1e-5f;                // :45
   t34_identity(p->T_init);
+  p->search_dir = CB_SECOND_TO_FIRST;  // correspondence_search_kd_tree.hpp:46-50
+  p->inlier_fraction = 1.0;
 }
 
 // mean of a cloud over all ranks (rowwise().mean(), icp_single_transform_combined_metric.hpp:51-58)
@@ -528,6 +532,7 @@ void cb_icp_destroy(cb_icp* icp) {
   cudaStreamSynchronize(icp->ctx->stream);
   if (icp->d_nn_pos) cudaFreeAsync(icp->d_nn_pos, icp->ctx->stream);
   if (icp->d_nn_d2) cudaFreeAsync(icp->d_nn_d2, icp->ctx->stream);
+  engine_release_pairs(icp->ctx, &icp->pairs);
   for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
   delete icp;
 }
@@ -572,8 +577,25 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   cb_context* ctx = icp->ctx;
   IcpArgs a;
   double sums[kMaxValues];
+  const bool engine = engine_mode(prm);
+  icp->engine_last = engine;
+  if (engine) {
+    // updateCorrespondences(): the explicit list (icp_engine.cu); the passes below accumulate over it
+    if (k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
+    CB_TRY(engine_find_pairs(ctx, icp->dst, icp->src, prm, T, &icp->pairs));
+    if (k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
+  }
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
     CB_TRY(icp_fill_args(icp, prm, T, nullptr, false, &a));
+    if (engine) {
+      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeP2P, false, false));
+      CB_TRY(icp_fetch(ctx, kP2PValues, sums));
+      kabsch_from_moments(sums, Titer);
+      *n_corr = sums[0];
+      icp->nn_valid = true;
+      icp->nn_stored = false;
+      return CB_OK;
+    }
     if (k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
     CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
     if (k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
@@ -593,12 +615,17 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   const bool bail_no_normals = w_pl_on && !dst_has_normals;
   const int max_opt = std::max(prm->max_opt_iter, 0);
   for (int it = 0; it < std::max(max_opt, 1); ++it) {
-    CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1, &a));
+    CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1 && !engine, &a));
     const bool search = (it == 0);
-    // the first pass always runs (it is also the correspondence search of this ICP iteration)
-    if (search && k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
-    CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
-    if (search && k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
+    if (engine) {
+      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeCombined, w_pt_on,
+                               w_pl_on && dst_has_normals));
+    } else {
+      // the first pass always runs (it is also the correspondence search of this ICP iteration)
+      if (search && k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
+      CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
+      if (search && k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
+    }
     CB_TRY(icp_fetch(ctx, kCombinedValues, sums));
     if (search) {
       *n_corr = sums[0];
@@ -737,6 +764,21 @@ int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_s
   CB_CUDA(cudaSetDevice(ctx->device));
   const size_t ns = icp->src->n;
   *count = 0;
+  if (icp->engine_last) {  // the list is already materialised, in the reference's order
+    const size_t m = icp->pairs.count;
+    if (m == 0) return CB_OK;
+    std::vector<uint32_t> f(m), s(m);
+    CB_CUDA(cudaMemcpyAsync(f.data(), icp->pairs.first, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaMemcpyAsync(s.data(), icp->pairs.second, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (value) CB_CUDA(cudaMemcpyAsync(value, icp->pairs.d2, m * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t k = 0; k < m; k++) {
+      if (index_first) index_first[k] = (uint64_t)f[k] + icp->dst->index_offset;
+      if (index_second) index_second[k] = (uint64_t)s[k] + icp->src->index_offset;
+    }
+    *count = m;
+    return CB_OK;
+  }
   if (ns == 0) return CB_OK;
   if (!icp->nn_stored) {  // re-run the last search, this time keeping the per-query result
     IcpArgs a{};

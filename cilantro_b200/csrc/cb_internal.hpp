@@ -155,6 +155,24 @@ int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out);
 bool arm_exchange(cb_context* ctx, Exchange* ex);
 int wait_exchange(cb_context* ctx, int count, double* out);
 
+// Correspondence list of the non-default engine modes (icp_engine.cu): device arrays of `count` pairs in
+// the reference's list order, ORIGINAL indices (first = dst point, second = src point).
+struct EnginePairs {
+  uint32_t* first = nullptr;
+  uint32_t* second = nullptr;
+  float* d2 = nullptr;
+  uint32_t count = 0;
+};
+inline bool engine_mode(const cb_icp_params* p) {
+  return p->search_dir != CB_SECOND_TO_FIRST || p->one_to_one != 0 ||
+         (p->inlier_fraction > 0.0 && p->inlier_fraction < 1.0);
+}
+// findCorrespondences(tform) of CorrespondenceSearchKDTree (correspondence_search_kd_tree.hpp:107-229) for
+// the current estimate T: searches, union / intersection, fraction and one-to-one filters. Replaces *pairs.
+int engine_find_pairs(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, const cb_icp_params* prm,
+                      const float* T12, EnginePairs* pairs);
+void engine_release_pairs(cb_context* ctx, EnginePairs* pairs);
+
 // nccl_dyn.cpp
 int nccl_unique_id(void* out128);
 int nccl_init(cb_context* ctx, const void* id128, int rank, int world);

@@ -41,6 +41,11 @@ struct IcpArgs {
 // Gauss-Newton iterations >= 2 keep the correspondences fixed, transform_estimation.hpp:281).
 int launch_icp_pass(cb_context* ctx, const IcpArgs& a, int mode, bool search, bool has_pt, bool has_pl);
 
+// Accumulation over an explicit correspondence list (non-default engine modes, icp_engine.cu): pair p =
+// (dst point first[p], src point second[p]) by ORIGINAL index; a supplies T, Tin, dm, sm, w_pt, w_pl.
+int launch_pairs_pass(cb_context* ctx, const IcpArgs& a, const EnginePairs& pairs, const cb_cloud* dst,
+                      const cb_cloud* src, int mode, bool has_pt, bool has_pl);
+
 // computeResiduals: unbounded 1-NN + the weighted residual, original query order.
 int launch_residuals(cb_context* ctx, const GridView& dst, const float4* src_pts, const float4* src_nrm,
                      uint32_t n_src, const Rigid& T, int metric, float w_pt, float w_pl, float* d_out);

@@ -292,8 +292,8 @@ private:
 // ---- ICP ---------------------------------------------------------------------------------------------
 enum struct CorrespondenceSearchDirection { FIRST_TO_SECOND, SECOND_TO_FIRST, BOTH };
 
-// The part of CorrespondenceSearchKDTree's fluent surface that the default SECOND_TO_FIRST path uses
-// (correspondence_search/correspondence_search_kd_tree.hpp:237-285).
+// CorrespondenceSearchKDTree's fluent surface (correspondence_search/correspondence_search_kd_tree.hpp:237-285).
+// The defaults run the fused kernel; any other setting goes through the device-side list (icp_engine.cu).
 class CorrespondenceSearchEngineB200 {
 public:
   using SearchResult = CorrespondenceSet<float, size_t>;
@@ -304,21 +304,43 @@ public:
   }
   const CorrespondenceSearchDirection& getSearchDirection() const { return dir_; }
   CorrespondenceSearchEngineB200& setSearchDirection(const CorrespondenceSearchDirection& d) {
-    if (d != CorrespondenceSearchDirection::SECOND_TO_FIRST)
-      throw std::runtime_error("cilantro_b200: only SECOND_TO_FIRST correspondence search is implemented");
     dir_ = d;
     return *this;
   }
-  double getInlierFraction() const { return 1.0; }
-  bool getRequireReciprocality() const { return false; }
-  bool getOneToOne() const { return false; }
+  double getInlierFraction() const { return inlier_fraction_; }
+  CorrespondenceSearchEngineB200& setInlierFraction(double fraction) {
+    inlier_fraction_ = fraction;
+    return *this;
+  }
+  bool getRequireReciprocality() const { return require_reciprocality_; }
+  CorrespondenceSearchEngineB200& setRequireReciprocality(bool require_reciprocal) {
+    require_reciprocality_ = require_reciprocal;
+    return *this;
+  }
+  bool getOneToOne() const { return one_to_one_; }
+  CorrespondenceSearchEngineB200& setOneToOne(bool one_to_one) {
+    one_to_one_ = one_to_one;
+    return *this;
+  }
   const SearchResult& getCorrespondences() const { return corr_; }
+  void fill(cb_icp_params& p) const {
+    p.max_d2 = max_distance_;
+    p.search_dir = dir_ == CorrespondenceSearchDirection::SECOND_TO_FIRST
+                       ? CB_SECOND_TO_FIRST
+                       : (dir_ == CorrespondenceSearchDirection::FIRST_TO_SECOND ? CB_FIRST_TO_SECOND : CB_BOTH);
+    p.inlier_fraction = inlier_fraction_;
+    p.require_reciprocal = require_reciprocality_ ? 1 : 0;
+    p.one_to_one = one_to_one_ ? 1 : 0;
+  }
 
 private:
   template <int>
   friend class SimpleRigidICP3fB200;
   float max_distance_ = (float)(0.01 * 0.01);  // correspondence_search_kd_tree.hpp:49
   CorrespondenceSearchDirection dir_ = CorrespondenceSearchDirection::SECOND_TO_FIRST;
+  double inlier_fraction_ = 1.0;
+  bool require_reciprocality_ = false;
+  bool one_to_one_ = false;
   SearchResult corr_;
 };
 
@@ -394,7 +416,7 @@ public:
   }
 
   SimpleRigidICP3fB200& estimate() {
-    prm_.max_d2 = engine_.max_distance_;
+    engine_.fill(prm_);
     b200::check(cb_icp_estimate(icp_, &prm_, &res_), "cb_icp_estimate");
     T_ = RigidTransform3f(res_.T);
     corr_fresh_ = false;
@@ -409,7 +431,7 @@ public:
   // correspondenceSearchEngine().getCorrespondences() after estimate(): materialised on demand
   const CorrespondenceSet<float, size_t>& getCorrespondences() {
     if (!corr_fresh_) {
-      const size_t n = cb_cloud_size(src_.h);
+      const size_t n = cb_cloud_size(src_.h) + cb_cloud_size(dst_.h);
       std::vector<uint64_t> a(n), b(n);
       std::vector<float> v(n);
       size_t cnt = 0;

@@ -184,7 +184,22 @@ typedef struct cb_icp_params {
                            iteration (kernel + exchange + host solve) -> gpu_ms_total / cb_icp_iteration_times,
                            2 one bracket per search kernel -> gpu_ms_search. Each cudaEventRecord costs a few us of
                            device front-end time, comparable to the ~100 us iteration, hence one mode at a time. */
+  /* Correspondence-engine options (correspondence_search_kd_tree.hpp:46-50, :60-98 setters). The defaults
+   * (SECOND_TO_FIRST, fraction 1, no reciprocity, not one-to-one) take the fused single-kernel path; any other
+   * setting materialises the correspondence list on the device (search(es) -> union / intersection -> fraction
+   * filter -> one-to-one filter, core/correspondence.hpp:57-100) and accumulates over it. Single GPU only. */
+  int32_t search_dir;          /* cb_search_dir; default CB_SECOND_TO_FIRST */
+  int32_t require_reciprocal;  /* with CB_BOTH: intersection instead of union (:68-70 of ..._utilities.hpp) */
+  int32_t one_to_one;          /* keep, per dst (SECOND_TO_FIRST) / src (FIRST_TO_SECOND) point, the closest pair */
+  int32_t reserved_;
+  double inlier_fraction;      /* keep the llround(fraction * M) closest pairs when 0 < fraction < 1; default 1 */
 } cb_icp_params;
+
+typedef enum cb_search_dir {
+  CB_SECOND_TO_FIRST = 0, /* queries = transformed src, tree = dst (the default) */
+  CB_FIRST_TO_SECOND = 1, /* queries = dst, tree = transformed src (rebuilt every iteration) */
+  CB_BOTH = 2
+} cb_search_dir;
 
 typedef struct cb_icp_result {
   float T[12];
@@ -204,7 +219,10 @@ void cb_icp_destroy(cb_icp* icp);
 int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res);
 /* Per-iteration device times of the last estimate() (ms); n = min(cap, iterations). */
 int cb_icp_iteration_times(cb_icp* icp, double* ms, int cap);
-/* getCorrespondences() of the engine after the last iteration (this rank's shard). */
+/* getCorrespondences() of the engine after the last iteration (this rank's shard). Arrays hold n_src entries
+ * (n_src + n_dst when search_dir == CB_BOTH). Default mode: ascending source index; other engine modes: the
+ * order the reference's filters leave (ascending value after the fraction filter, ascending dst / src index
+ * after the one-to-one filter, lexicographic (first, second) for CB_BOTH). */
 int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_second, float* value,
                            size_t* count);
 /* computeResiduals() — icp_single_transform_combined_metric.hpp:220-243 /

@@ -49,7 +49,15 @@ class IcpParams(C.Structure):
         ("accum_double", C.c_int32),
         ("parallel", C.c_int32),
         ("T_init", C.c_float * 12),
+        ("search_dir", C.c_int32),
+        ("require_reciprocal", C.c_int32),
+        ("one_to_one", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("inlier_fraction", C.c_double),
     ]
+
+
+SEARCH_DIR = {"second_to_first": 0, "first_to_second": 1, "both": 2}
 
 
 class IcpResult(C.Structure):
@@ -294,12 +302,13 @@ def estimate_combined(dst_p, dst_n, src_p, idx_first, idx_second, w_pt, w_pl, ma
 
 def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, tol=1e-5, max_d2=1e-4,
         w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5, T_init=None, accum_double=False, parallel=False,
-        log=False):
+        log=False, search_dir="second_to_first", inlier_fraction=1.0, require_reciprocal=False, one_to_one=False):
     """icp_base.hpp:68-87 driving the p2p or combined/symmetric estimator. Returns a dict."""
     dst_p, src_p = _f32(dst_p), _f32(src_p)
     dst_n = _f32(dst_n) if dst_n is not None else None
     src_n = _f32(src_n) if src_n is not None else None
     prm = IcpParams()
+    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one)
     prm.metric = 0 if metric == "p2p" else 1
     prm.max_iter = int(max_iter)
     prm.tol = tol
@@ -330,6 +339,30 @@ def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, to
     if log:
         out["T_log"] = tlog[: res.iterations]
     return out
+
+
+def _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one):
+    prm.search_dir = SEARCH_DIR[search_dir] if isinstance(search_dir, str) else int(search_dir)
+    prm.inlier_fraction = float(inlier_fraction)
+    prm.require_reciprocal = int(require_reciprocal)
+    prm.one_to_one = int(one_to_one)
+
+
+def engine_correspondences(dst_p, src_p, T, knn, max_d2, search_dir="second_to_first", inlier_fraction=1.0,
+                           require_reciprocal=False, one_to_one=False):
+    """CorrespondenceSearchKDTree::findCorrespondences(T).getCorrespondences(): (first, second, value)."""
+    dst_p, src_p = _f32(dst_p), _f32(src_p)
+    prm = IcpParams()
+    prm.max_d2 = max_d2
+    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one)
+    cap = dst_p.shape[0] + src_p.shape[0]
+    i1 = np.empty(cap, np.uint64)
+    i2 = np.empty(cap, np.uint64)
+    v = np.empty(cap, np.float32)
+    lib().orc_engine_correspondences.restype = C.c_size_t
+    m = lib().orc_engine_correspondences(_p(dst_p), C.c_size_t(dst_p.shape[0]), _p(src_p), C.c_size_t(src_p.shape[0]),
+                                         _p(_T(T)), C.byref(prm), knn.fn, knn.user, _p(i1), _p(i2), _p(v))
+    return i1[:m].astype(np.int64), i2[:m].astype(np.int64), v[:m].copy()
 
 
 def icp_residuals(dst_p, src_p, T, knn, metric="p2p", dst_n=None, src_n=None, w_pt=0.0, w_pl=1.0):

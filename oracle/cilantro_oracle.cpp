@@ -501,7 +501,84 @@ struct orc_icp_params {
   int32_t accum_double;  // 0 = faithful fp32 accumulation, 1 = double accumulation
   int32_t parallel;      // 1 = ENABLE_NON_DETERMINISTIC_PARALLELISM-style OpenMP reduction (timing runs)
   float T_init[12];      // icp_base.hpp:58-61
+  // correspondence-engine options (correspondence_search_kd_tree.hpp:46-50); defaults 0, 0, 0, 1.0
+  int32_t search_dir;          // 0 SECOND_TO_FIRST, 1 FIRST_TO_SECOND, 2 BOTH
+  int32_t require_reciprocal;
+  int32_t one_to_one;
+  int32_t reserved_;
+  double inlier_fraction;
 };
+
+// CorrespondenceSearchKDTree::findCorrespondences(tform) — correspondence_search_kd_tree.hpp:107-229:
+//   SECOND_TO_FIRST (:205-213)  queries = transformed src against the dst tree (the knn callback)
+//   FIRST_TO_SECOND (:195-204)  queries = dst against a tree over the transformed src, rebuilt per call —
+//                               restated by brute force (orc_knn1_brute: same distance arithmetic, lowest
+//                               index on exact ties); small inputs only
+//   BOTH (:214-226)             both lists sorted lexicographically on (first, second), then set_union, or
+//                               set_intersection when require_reciprocal
+//                               (correspondence_search_kd_tree_utilities.hpp:64-99)
+//   filterCorrespondencesFraction (core/correspondence.hpp:57-66): sort by value, keep llround(f * size)
+//   filterCorrespondencesOneToOne (:68-100): sort by (index, value), keep the first pair per index
+// std::sort leaves equal keys in unspecified order; stable_sort pins the rule shared with the CUDA path:
+// ties keep the order of the list the filter received.
+static void engine_correspondences(const float* dst_p, size_t n_dst, const float* src_trans, size_t n_src,
+                                   const orc_icp_params* prm, orc_knn_fn knn, void* knn_user,
+                                   std::vector<Corr>& corr, std::vector<int64_t>& idx, std::vector<float>& d2) {
+  std::vector<Corr> s2f, f2s;
+  const int dir = prm->search_dir;
+  if (dir != 1) find_correspondences(src_trans, n_src, n_dst, prm->max_d2, knn, knn_user, s2f, idx, d2);
+  if (dir != 0 && n_src > 0 && n_dst > 0) {
+    std::vector<int64_t> j(n_dst);
+    std::vector<float> v(n_dst);
+    orc_knn1_brute(src_trans, n_src, dst_p, n_dst, prm->max_d2, j.data(), v.data());
+    for (size_t i = 0; i < n_dst; i++)
+      if (j[i] >= 0 && v[i] < prm->max_d2) f2s.push_back({i, (size_t)j[i], v[i]});
+  }
+  auto lex = [](const Corr& a, const Corr& b) {
+    return a.indexInFirst != b.indexInFirst ? a.indexInFirst < b.indexInFirst : a.indexInSecond < b.indexInSecond;
+  };
+  corr.clear();
+  if (dir == 0) {
+    corr = s2f;
+  } else if (dir == 1) {
+    corr = f2s;
+  } else {
+    std::sort(f2s.begin(), f2s.end(), lex);
+    std::sort(s2f.begin(), s2f.end(), lex);
+    if (prm->require_reciprocal)
+      std::set_intersection(f2s.begin(), f2s.end(), s2f.begin(), s2f.end(), std::back_inserter(corr), lex);
+    else
+      std::set_union(f2s.begin(), f2s.end(), s2f.begin(), s2f.end(), std::back_inserter(corr), lex);
+  }
+  const double f = prm->inlier_fraction;
+  if (f > 0.0 && f < 1.0) {
+    std::stable_sort(corr.begin(), corr.end(), [](const Corr& a, const Corr& b) { return a.value < b.value; });
+    corr.erase(corr.begin() + std::llround(f * (double)corr.size()), corr.end());
+  }
+  if (prm->one_to_one && !corr.empty() && dir != 2) {
+    std::vector<Corr> copy = corr;
+    corr.clear();
+    if (dir == 1) {
+      std::stable_sort(copy.begin(), copy.end(), [](const Corr& a, const Corr& b) {
+        return a.indexInSecond != b.indexInSecond ? a.indexInSecond < b.indexInSecond : a.value < b.value;
+      });
+      corr.push_back(copy.front());
+      for (const Corr& c : copy)
+        if (c.indexInSecond != corr.back().indexInSecond) corr.push_back(c);
+    } else {
+      std::stable_sort(copy.begin(), copy.end(), [](const Corr& a, const Corr& b) {
+        return a.indexInFirst != b.indexInFirst ? a.indexInFirst < b.indexInFirst : a.value < b.value;
+      });
+      corr.push_back(copy.front());
+      for (const Corr& c : copy)
+        if (c.indexInFirst != corr.back().indexInFirst) corr.push_back(c);
+    }
+  }
+}
+
+static bool engine_mode(const orc_icp_params* p) {
+  return p->search_dir != 0 || p->one_to_one != 0 || (p->inlier_fraction > 0.0 && p->inlier_fraction < 1.0);
+}
 
 struct orc_icp_result {
   float T[12];
@@ -543,7 +620,10 @@ ORC_API void orc_icp(const float* dst_p, const float* dst_n, size_t n_dst, const
     auto t0 = clk::now();
     // updateCorrespondences(): transformFeatures(T) then the radius-bounded 1-NN sweep
     orc_transform_points(T.m, src_p, n_src, src_trans.data());
-    find_correspondences(src_trans.data(), n_src, n_dst, prm->max_d2, knn, knn_user, corr, idx, d2);
+    if (engine_mode(prm))
+      engine_correspondences(dst_p, n_dst, src_trans.data(), n_src, prm, knn, knn_user, corr, idx, d2);
+    else
+      find_correspondences(src_trans.data(), n_src, n_dst, prm->max_d2, knn, knn_user, corr, idx, d2);
     auto t1 = clk::now();
     // updateEstimate(): transformPoints(T, src) again (same values), then the estimator
     T34 Titer;
@@ -594,6 +674,24 @@ ORC_API void orc_icp(const float* dst_p, const float* dst_n, size_t n_dst, const
   res->last_num_corr = corr.size();
   res->t_knn_s = t_knn;
   res->t_est_s = t_est;
+}
+
+// getCorrespondences() after findCorrespondences(T) with the engine options of prm (tests).
+ORC_API size_t orc_engine_correspondences(const float* dst_p, size_t n_dst, const float* src_p, size_t n_src,
+                                          const float* T12, const orc_icp_params* prm, orc_knn_fn knn,
+                                          void* knn_user, uint64_t* idx_first, uint64_t* idx_second, float* value) {
+  std::vector<float> q(3 * n_src);
+  orc_transform_points(T12, src_p, n_src, q.data());
+  std::vector<Corr> corr;
+  std::vector<int64_t> idx;
+  std::vector<float> d2;
+  engine_correspondences(dst_p, n_dst, q.data(), n_src, prm, knn, knn_user, corr, idx, d2);
+  for (size_t i = 0; i < corr.size(); i++) {
+    idx_first[i] = corr[i].indexInFirst;
+    idx_second[i] = corr[i].indexInSecond;
+    value[i] = corr[i].value;
+  }
+  return corr.size();
 }
 
 // computeResiduals() — icp_single_transform_combined_metric.hpp:220-243 (metric 1) and

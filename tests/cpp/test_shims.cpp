@@ -173,6 +173,26 @@ int main() {
     std::printf("p2p ICP: %zu iterations, |T - tf_ref^-1|_F = %.2e\n", icp.getNumberOfPerformedIterations(),
                 frob(icp.getTransform(), tf_ref.inverse()));
     CHECK(frob(icp.getTransform(), tf_ref.inverse()) < 5e-2f);
+    // non-default engine modes (correspondence_search_kd_tree.hpp:237-285): reciprocal pairs, closest 80 %
+    cilantro::SimplePointToPointMetricRigidICP3f icp2(dst.points, src.points);
+    icp2.correspondenceSearchEngine()
+        .setMaxDistance(0.3f * 0.3f)
+        .setSearchDirection(cilantro::CorrespondenceSearchDirection::BOTH)
+        .setRequireReciprocality(true)
+        .setInlierFraction(0.8);
+    icp2.setInitialTransform(icp.getTransform()).setMaxNumberOfIterations(10).setConvergenceTolerance(1e-6f).estimate();
+    const auto& corr = icp2.getCorrespondences();
+    std::printf("reciprocal + fraction ICP: %zu iterations, %zu pairs, |T - tf_ref^-1|_F = %.2e\n",
+                icp2.getNumberOfPerformedIterations(), corr.size(), frob(icp2.getTransform(), tf_ref.inverse()));
+    CHECK(corr.size() > N / 4 && corr.size() <= N);
+    for (size_t i = 1; i < corr.size(); i++) CHECK(corr[i - 1].value <= corr[i].value);  // sorted by the fraction filter
+    CHECK(frob(icp2.getTransform(), tf_ref.inverse()) < 5e-2f);
+    cilantro::SimplePointToPointMetricRigidICP3f icp3(dst.points, src.points);
+    icp3.correspondenceSearchEngine().setMaxDistance(0.3f * 0.3f).setOneToOne(true);
+    icp3.setInitialTransform(icp.getTransform()).setMaxNumberOfIterations(3).estimate();
+    const auto& c3 = icp3.getCorrespondences();
+    CHECK(!c3.empty());
+    for (size_t i = 1; i < c3.size(); i++) CHECK(c3[i - 1].indexInFirst < c3[i].indexInFirst);  // one pair per dst point
   }
   // ---- kmeans.cpp ------------------------------------------------------------------------------------------
   {
