@@ -13,8 +13,10 @@
 //   KMeans3f<>                                              clustering/kmeans.hpp:9-59,205-207
 //   RigidTransformRANSACEstimator3f<>                       model_estimation/ransac_transform_estimator.hpp:9-122
 //   PrincipalComponentAnalysis3f                            core/principal_component_analysis.hpp:8-89
-//   PointCloud3f (points / normals / colors, size, hasNormals, transform)
-//                                                           utilities/point_cloud.hpp:14-22,557
+//   NormalEstimation3f                                      core/normal_estimation.hpp:11-421
+//   Points[Normals][Colors]GridDownsampler3f                core/grid_downsampler.hpp:8-340
+//   PointCloud3f (points / normals / colors, size, hasNormals, transform, gridDownsample[d],
+//                 estimateNormals{KNN,Radius,KNNInRadius})  utilities/point_cloud.hpp:14-22,246-420,557
 //   Timer                                                   utilities/timer.hpp
 // Eigen3 is an external dependency of cilantro that is absent from the build image, so the containers
 // below are minimal Eigen-free stand-ins with the memory layout cilantro uses (column-major 3 x N,
