@@ -81,7 +81,7 @@ EXPORTED = [
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
     "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
-    "cb_knn1_radius", "cb_knn_radius", "cb_find_correspondences",
+    "cb_knn1_radius", "cb_knn_radius", "cb_radius_search", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
     "cb_icp_correspondences", "cb_icp_residuals", "cb_icp_accumulate",
     "cb_solve_kabsch_moments", "cb_solve_gauss_newton", "cb_solve_rotation", "cb_compose",
@@ -278,6 +278,22 @@ class Cloud:
         occ = C.c_double()
         _check(lib().cb_cloud_grid_info(self.h, C.byref(edge), dims, C.byref(occ)))
         return {"cell_edge": edge.value, "dims": list(dims), "mean_occupancy": occ.value}
+
+
+def radius_search(ctx, ref, qry, radius2, T=None):
+    """cb_radius_search: CSR (offsets [nq + 1], idx, d2) of all ref points with d2 < radius2 per query."""
+    offsets = np.zeros(qry.n + 1, np.uint64)
+    total = C.c_size_t()
+    Tm = _T(T) if T is not None else None
+    _check(lib().cb_radius_search(ctx.h, ref.h, qry.h, _p(Tm), C.c_float(radius2), _p(offsets), None, None,
+                                  C.c_size_t(0), C.byref(total)))
+    m = total.value
+    idx = np.empty(m, np.int64)
+    d2 = np.empty(m, np.float32)
+    if m:
+        _check(lib().cb_radius_search(ctx.h, ref.h, qry.h, _p(Tm), C.c_float(radius2), _p(offsets), _p(idx), _p(d2),
+                                      C.c_size_t(m), C.byref(total)))
+    return offsets.astype(np.int64), idx, d2
 
 
 def grid_downsample(ctx, xyz, bin_size, normals=None, colors=None, min_points=1, order=0):

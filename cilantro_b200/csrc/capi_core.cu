@@ -367,6 +367,7 @@ void cb_cloud_destroy(cb_cloud* c) {
   if (c->d_pts) cudaFreeAsync(c->d_pts, c->ctx->stream);
   if (c->d_nrm) cudaFreeAsync(c->d_nrm, c->ctx->stream);
   if (c->d_cell_start) cudaFreeAsync(c->d_cell_start, c->ctx->stream);
+  if (c->d_blocks) cudaFreeAsync(c->d_blocks, c->ctx->stream);
   delete c;
 }
 

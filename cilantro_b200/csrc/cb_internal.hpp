@@ -80,7 +80,14 @@ struct GridView {
   float h_safe;                // cell edge * (1 - 2^-10): conservative edge for lower bounds
   int nx, ny, nz;
   uint32_t n;
+  // Non-empty coarse blocks (kBlockCells^3 cells each): x = X, y = Y, z = Z block coordinates, w = number
+  // of points. Only the far-query path (far_sweep.cuh) reads them: queries that would have to cross a lot of
+  // empty space shell by shell iterate this list instead.
+  const uint4* blocks;
+  uint32_t nblocks;
 };
+
+constexpr int kBlockCells = 8;  // coarse block edge in cells
 
 }  // namespace cb
 
@@ -131,6 +138,8 @@ struct cb_cloud {
   float4* d_pts = nullptr;
   float4* d_nrm = nullptr;
   uint32_t* d_cell_start = nullptr;
+  uint4* d_blocks = nullptr;  // non-empty coarse blocks (GridView::blocks)
+  uint32_t nblocks = 0;
   float ox = 0, oy = 0, oz = 0, h = 1, inv_h = 1;
   int nx = 1, ny = 1, nz = 1;
   double mean_occ = 0;

@@ -271,6 +271,37 @@ __global__ void gather_kernel(const float* __restrict__ raw, const float* __rest
   }
 }
 
+// points per coarse block (kBlockCells^3 cells): 64 row ranges of the final cell_start table
+__global__ void block_count_kernel(const uint32_t* __restrict__ cell_start, int nx, int ny, int nz, int bx, int by,
+                                   int bz, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flag) {
+  const size_t nb = (size_t)bx * by * bz;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b <= nb; b += (size_t)gridDim.x * blockDim.x) {
+    if (b == nb) {
+      flag[b] = 0u;
+      continue;
+    }
+    const int X = (int)(b % bx), Y = (int)((b / bx) % by), Z = (int)(b / ((size_t)bx * by));
+    const int x0 = X * kBlockCells, x1 = min(x0 + kBlockCells, nx);
+    uint32_t c = 0;
+    for (int z = Z * kBlockCells; z < min((Z + 1) * kBlockCells, nz); ++z)
+      for (int y = Y * kBlockCells; y < min((Y + 1) * kBlockCells, ny); ++y) {
+        const size_t base = ((size_t)z * ny + y) * nx;
+        c += cell_start[base + x1] - cell_start[base + x0];
+      }
+    cnt[b] = c;
+    flag[b] = c > 0 ? 1u : 0u;
+  }
+}
+
+__global__ void block_emit_kernel(const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ scanned, int bx,
+                                  int by, int bz, uint4* __restrict__ blocks) {
+  const size_t nb = (size_t)bx * by * bz;
+  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < nb; b += (size_t)gridDim.x * blockDim.x) {
+    if (cnt[b] == 0) continue;
+    blocks[scanned[b]] = make_uint4((unsigned)(b % bx), (unsigned)((b / bx) % by), (unsigned)(b / ((size_t)bx * by)), cnt[b]);
+  }
+}
+
 inline int grid_blocks(const cb_context* ctx, size_t n, int per_sm = 8) {
   size_t want = (n + kThreads - 1) / kThreads;
   size_t cap = (size_t)ctx->sm_count * per_sm;
@@ -429,6 +460,27 @@ int ensure_index(cb_cloud* c) {
   ctx->launches += 4;
   CB_CUDA(cudaGetLastError());
   c->d_cell_start = d_hist;  // keeps (ncells + 1) entries; freed with cudaFree in cb_cloud_destroy
+  // 6. coarse occupancy: the list of non-empty 8x8x8-cell blocks for the far-query path
+  {
+    const int bx = (gp.nx + kBlockCells - 1) / kBlockCells, by = (gp.ny + kBlockCells - 1) / kBlockCells,
+              bz = (gp.nz + kBlockCells - 1) / kBlockCells;
+    const size_t nb = (size_t)bx * by * bz;
+    uint32_t* d_cnt = nullptr;
+    CB_CUDA(cudaMallocAsync(&d_cnt, (2 * nb + 2) * sizeof(uint32_t), ctx->stream));
+    uint32_t* d_flag = d_cnt + nb;  // nb + 2 entries
+    block_count_kernel<<<grid_blocks(ctx, nb), kThreads, 0, ctx->stream>>>(d_hist, gp.nx, gp.ny, gp.nz, bx, by, bz,
+                                                                         d_cnt, d_flag);
+    CB_TRY(exclusive_scan_u32(ctx, d_flag, nb + 1, 0u));
+    uint32_t nblocks = 0;
+    CB_CUDA(cudaMemcpyAsync(&nblocks, d_flag + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    CB_CUDA(cudaMallocAsync(&c->d_blocks, std::max<size_t>(nblocks, 1) * sizeof(uint4), ctx->stream));
+    block_emit_kernel<<<grid_blocks(ctx, nb), kThreads, 0, ctx->stream>>>(d_cnt, d_flag, bx, by, bz, c->d_blocks);
+    ctx->launches += 2;
+    CB_CUDA(cudaGetLastError());
+    c->nblocks = nblocks;
+    CB_CUDA(cudaFreeAsync(d_cnt, ctx->stream));
+  }
   CB_CUDA(cudaFreeAsync(d_cell_id, ctx->stream));
   CB_CUDA(cudaFreeAsync(d_stats, ctx->stream));
   CB_CUDA(cudaFreeAsync(d_cursor, ctx->stream));
@@ -454,6 +506,8 @@ GridView grid_view(const cb_cloud* c) {
   g.ny = c->ny;
   g.nz = c->nz;
   g.n = (uint32_t)c->n;
+  g.blocks = c->d_blocks;
+  g.nblocks = c->nblocks;
   return g;
 }
 

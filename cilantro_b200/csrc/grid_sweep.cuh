@@ -4,14 +4,17 @@
 // shrink while scanning (k-best lists) or stay constant (radius neighbourhoods).
 //   bound(): float      current admissible squared distance (strict: candidates need d2 < bound)
 //   scan(b, e)          consume the cell-sorted points [b, e)
+//   reset()             forget everything consumed so far (the sweep restarts on the far-query path,
+//                       far_sweep.cuh, when crossing empty space shell by shell gets too expensive)
+//   k_needed            how many neighbours the caller is after (0 = all within a fixed bound)
 #pragma once
 #include "nn_search.cuh"
 
 namespace cb {
 
-template <class BoundFn, class ScanFn>
+template <class BoundFn, class ScanFn, class ResetFn>
 __device__ __forceinline__ void grid_sweep(const GridView& g, float qx, float qy, float qz, BoundFn bound,
-                                           ScanFn scan) {
+                                           ScanFn scan, ResetFn reset, uint32_t k_needed) {
   if (g.n == 0) return;
   const float fx = cell_coord(qx, g.ox, g.inv_h), fy = cell_coord(qy, g.oy, g.inv_h),
               fz = cell_coord(qz, g.oz, g.inv_h);
@@ -21,6 +24,7 @@ __device__ __forceinline__ void grid_sweep(const GridView& g, float qx, float qy
   k0 = max(k0, cx < 0 ? -cx : (cx > g.nx - 1 ? cx - (g.nx - 1) : 0));
   k0 = max(k0, cy < 0 ? -cy : (cy > g.ny - 1 ? cy - (g.ny - 1) : 0));
   k0 = max(k0, cz < 0 ? -cz : (cz > g.nz - 1 ? cz - (g.nz - 1) : 0));
+  int row_budget = kFarRowBudget;
   for (int sh = k0;; ++sh) {
     if (sh > 0) {
       // termination: distance to the nearest unscanned face vs the bound (a point beyond the face
@@ -40,6 +44,12 @@ __device__ __forceinline__ void grid_sweep(const GridView& g, float qx, float qy
     }
     const int z0 = max(cz - sh, 0), z1 = min(cz + sh, g.nz - 1);
     const int y0 = max(cy - sh, 0), y1 = min(cy + sh, g.ny - 1);
+    row_budget -= (z1 - z0 + 1) * (y1 - y0 + 1);
+    if (row_budget < 0) {
+      reset();
+      far_sweep(g, qx, qy, qz, k_needed, bound, scan);
+      return;
+    }
     const int xl = cx - sh, xr = cx + sh;
     const int x0 = max(xl, 0), x1 = min(xr, g.nx - 1);
     for (int rz = z0; rz <= z1; ++rz) {

@@ -315,6 +315,7 @@ int engine_find_pairs(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src,
     if (moved.d_raw) cudaFreeAsync(moved.d_raw, ctx->stream);
     if (moved.d_pts) cudaFreeAsync(moved.d_pts, ctx->stream);
     if (moved.d_cell_start) cudaFreeAsync(moved.d_cell_start, ctx->stream);
+    if (moved.d_blocks) cudaFreeAsync(moved.d_blocks, ctx->stream);
     CB_TRY(rc);
   }
   // pre-filter list

@@ -129,6 +129,12 @@ __device__ __forceinline__ float slab_gap(float f, int c, int r) {
   return g > 0.f ? g : 0.f;
 }
 
+}  // namespace cb
+
+#include "far_sweep.cuh"
+
+namespace cb {
+
 // Exact nearest neighbour of (qx,qy,qz) among the grid's points with d2 < max_d2.
 template <bool kExact>
 __device__ __forceinline__ Best grid_nearest_impl(const GridView& g, float qx, float qy, float qz, float max_d2) {
@@ -212,6 +218,7 @@ __device__ __forceinline__ Best grid_nearest_impl(const GridView& g, float qx, f
     // fall through to the termination test with k-1 = 1 completed shells
   }
 
+  int row_budget = kFarRowBudget;
 #pragma unroll 1
   for (;; ++k) {
     // Shells < k are done. Distance (cells) from the query to the nearest face of the scanned
@@ -235,6 +242,18 @@ __device__ __forceinline__ Best grid_nearest_impl(const GridView& g, float qx, f
     // Shell k: rows with max(|dy|,|dz|) == k take the full x-extent, inner rows only the two end cells.
     const int z0 = max(cz - k, 0), z1 = min(cz + k, g.nz - 1);
     const int y0 = max(cy - k, 0), y1 = min(cy + k, g.ny - 1);
+    row_budget -= (z1 - z0 + 1) * (y1 - y0 + 1);
+    if (row_budget < 0) {
+      // too much (mostly empty) space crossed shell by shell: restart on the list of non-empty blocks
+      best.d2 = max_d2;
+      best.idx = -1;
+      best.pos = -1;
+      best.tie = false;
+      far_sweep(
+          g, qx, qy, qz, 1u, [&]() { return best.d2; },
+          [&](uint32_t b, uint32_t e) { scan_range<kExact>(g.pts, b, e, qx, qy, qz, best); });
+      break;
+    }
     const int xl = cx - k, xr = cx + k;
     const int x0 = max(xl, 0), x1 = min(xr, g.nx - 1);
     for (int rz = z0; rz <= z1; ++rz) {

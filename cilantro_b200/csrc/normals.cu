@@ -176,7 +176,13 @@ __global__ void __launch_bounds__(kBlock) normals_knn_kernel(const GridView g, i
         if (count == k) worst = sd[k - 1][t];
       }
     };
-    grid_sweep(g, s.x, s.y, s.z, bound, scan);
+    grid_sweep(
+        g, s.x, s.y, s.z, bound, scan,
+        [&]() {
+          count = 0;
+          worst = max_d2;
+        },
+        (uint32_t)k);
     float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool valid = count >= 3;  // setMinValidSampleSize(points_.rows()), normal_estimation.hpp:27
     if (valid) {
@@ -233,7 +239,10 @@ __global__ void __launch_bounds__(kBlock) normals_radius_kernel(const GridView g
           ++count;
         }
       }
-    });
+    }, [&]() {
+      count = 0;
+      mx = my = mz = 0.f;
+    }, 0u);
     float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const bool valid = count >= 3;
     if (valid) {
@@ -254,7 +263,10 @@ __global__ void __launch_bounds__(kBlock) normals_radius_kernel(const GridView g
             cv[5] = __fadd_rn(cv[5], __fmul_rn(dz, dz));
           }
         }
-      });
+      }, [&]() {
+#pragma unroll
+        for (int c = 0; c < 6; c++) cv[c] = 0.f;
+      }, 0u);
       const float invm1 = __fdiv_rn(1.0f, (float)(count - 1));
 #pragma unroll
       for (int c = 0; c < 6; c++) cv[c] = __fmul_rn(invm1, cv[c]);

@@ -155,6 +155,24 @@ using NeighborSet = std::vector<Neighbor<ScalarT, IndexT>>;
 template <typename ScalarT = float, typename IndexT = size_t>
 using Neighborhood = NeighborSet<ScalarT, IndexT>;
 
+// neighbourhood specifications (core/nearest_neighbors.hpp:58-87); radii are squared distances
+template <typename CountT = size_t>
+struct KNNNeighborhoodSpecification {
+  KNNNeighborhoodSpecification(CountT k = (CountT)0) : maxNumberOfNeighbors(k) {}
+  CountT maxNumberOfNeighbors;
+};
+template <typename ScalarT>
+struct RadiusNeighborhoodSpecification {
+  RadiusNeighborhoodSpecification(ScalarT r = (ScalarT)0) : radius(r) {}
+  ScalarT radius;
+};
+template <typename ScalarT, typename CountT = size_t>
+struct KNNInRadiusNeighborhoodSpecification {
+  KNNInRadiusNeighborhoodSpecification(CountT k = 0, ScalarT r = (ScalarT)0) : maxNumberOfNeighbors(k), radius(r) {}
+  CountT maxNumberOfNeighbors;
+  ScalarT radius;
+};
+
 template <typename ScalarT = float, typename IndexT = size_t>
 struct Correspondence {
   IndexT indexInFirst;
@@ -282,6 +300,46 @@ public:
       for (uint32_t j = 0; j < cnt[i]; j++) out[i][j] = {static_cast<IndexT>(idx[i * k + j]), d2[i * k + j]};
     }
     return out;
+  }
+  // radiusSearch (core/kd_tree.hpp:250-278): every point with squared distance < radius, ascending distance
+  NeighborhoodSetResult radiusSearch(const ConstVectorSetMatrixMap3f& queries, float radius) const {
+    const size_t nq = queries.cols();
+    NeighborhoodSetResult out(nq);
+    if (nq == 0 || n_ == 0) return out;
+    b200::CloudHandle q(queries);
+    std::vector<uint64_t> off(nq + 1);
+    size_t total = 0;
+    b200::check(cb_radius_search(b200::Context::get(), cloud_.h, q.h, nullptr, radius, off.data(), nullptr, nullptr, 0,
+                                 &total),
+                "cb_radius_search");
+    if (total == 0) return out;
+    std::vector<int64_t> idx(total);
+    std::vector<float> d2(total);
+    b200::check(cb_radius_search(b200::Context::get(), cloud_.h, q.h, nullptr, radius, off.data(), idx.data(), d2.data(),
+                                 total, &total),
+                "cb_radius_search");
+    for (size_t i = 0; i < nq; i++) {
+      out[i].resize(off[i + 1] - off[i]);
+      for (size_t j = off[i]; j < off[i + 1]; j++) out[i][j - off[i]] = {static_cast<IndexT>(idx[j]), d2[j]};
+    }
+    return out;
+  }
+  NeighborhoodResult radiusSearch(const Vector3f& q, float radius) const {
+    NeighborhoodSetResult r = radiusSearch(ConstVectorSetMatrixMap3f(q.data(), 1), radius);
+    return r.empty() ? NeighborhoodResult() : r[0];
+  }
+  // search(query / queries, neighbourhood specification) (core/kd_tree.hpp:320-381)
+  template <typename QueryT, typename CountT>
+  auto search(const QueryT& q, const KNNNeighborhoodSpecification<CountT>& nh) const {
+    return kNNSearch(q, (size_t)nh.maxNumberOfNeighbors);
+  }
+  template <typename QueryT>
+  auto search(const QueryT& q, const RadiusNeighborhoodSpecification<float>& nh) const {
+    return radiusSearch(q, nh.radius);
+  }
+  template <typename QueryT, typename CountT>
+  auto search(const QueryT& q, const KNNInRadiusNeighborhoodSpecification<float, CountT>& nh) const {
+    return kNNInRadiusSearch(q, (size_t)nh.maxNumberOfNeighbors, nh.radius);
   }
   const ConstVectorSetMatrixMap3f& getPointsMatrixMap() const { return data_map_; }  // core/kd_tree.hpp:172-174
 

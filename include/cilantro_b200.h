@@ -110,6 +110,13 @@ int cb_knn1_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, co
  * idx/d2 are n_qry x k, ascending d2, unused slots idx = -1. counts (may be NULL) = found per query. */
 int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, int k,
                   float max_d2, int64_t* idx, float* d2, uint32_t* counts);
+/* KDTree::radiusSearch batched (core/kd_tree.hpp:250-278): for query i, every ref point with d2 < radius2,
+ * ascending d2 (equal distances: ascending index; the reference leaves them to std::sort), as a CSR list:
+ * entries offsets[i] .. offsets[i+1]-1 of idx / d2; offsets has n_qry + 1 entries. *total = offsets[n_qry].
+ * Sizing: call with idx = d2 = NULL (or a too small capacity) -> offsets and *total are filled, nothing else
+ * is written; call again with buffers of capacity >= *total. */
+int cb_radius_search(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, float radius2,
+                     uint64_t* offsets, int64_t* idx, float* d2, size_t capacity, size_t* total);
 /* ---- normal / curvature estimation -------------------------------------------------------------
  * Replaces NormalEstimation::estimateNormalsAndCurvature{KNN,Radius,KNNInRadius} (core/
  * normal_estimation.hpp:83-232 -> compute_normals_curvature_* :357-421) as called by

@@ -451,13 +451,17 @@ def ransac_rigid(dst, src, seed, max_iter=100, thresh=0.01, inlier_count_thresh=
 FLT_MAX = float(np.finfo(np.float32).max)
 
 
-def estimate_normals(pts, knn, k=0, radius2=None, view_point=None, ref_normals=None):
+def estimate_normals(pts, knn, k=0, radius2=None, view_point=None, ref_normals=None, neighbors=None):
     """NormalEstimation::estimateNormalsAndCurvature{KNN,Radius,KNNInRadius} (core/normal_estimation.hpp:83-232)
-    on neighbourhoods from `knn` (RefKnn = the reference's nanoflann). Returns normals, curvature, cov6, cnt."""
+    on neighbourhoods from `knn` (RefKnn = the reference's nanoflann), or on precomputed `neighbors` = (idx, cnt).
+    Returns normals, curvature, cov6, cnt."""
     pts = _f32(pts)
     n = pts.shape[0]
     r2 = FLT_MAX if radius2 is None else float(radius2)
-    if k > 0:
+    if neighbors is not None:
+        idx = np.ascontiguousarray(neighbors[0], np.int64)
+        cnt = np.ascontiguousarray(neighbors[1], np.uint32)
+    elif k > 0:
         idx, _, cnt = knn.neighborhoods(pts, k, r2)
     else:
         _, _, cnt = knn.neighborhoods(pts, 0, r2, stride=1)

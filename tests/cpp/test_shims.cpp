@@ -57,6 +57,14 @@ int main() {
     CHECK(nn[0].index == 0 && nn[1].index == 3);
     CHECK(std::fabs(nn[0].value - 0.18f) < 1e-6f && std::fabs(nn[1].value - 0.38f) < 1e-6f);
     CHECK(tree.nearestNeighborSearch(cilantro::Vector3f(0.9f, 0.9f, 0.8f)).index == 7);
+    // radiusSearch / search(spec): squared radius, ascending distance, equal distances by index
+    cilantro::NeighborSet<float> rn = tree.radiusSearch(cilantro::Vector3f(0.1f, 0.1f, 0.4f), 1.0f);
+    CHECK(rn.size() == 4 && rn[0].index == 0 && rn[1].index == 3 && rn[2].index == 1 && rn[3].index == 2);
+    CHECK(rn[2].value == rn[3].value && std::fabs(rn[2].value - 0.98f) < 1e-6f);
+    CHECK(tree.search(cilantro::Vector3f(0.1f, 0.1f, 0.4f), cilantro::RadiusNeighborhoodSpecification<float>(0.2f)).size() == 1);
+    CHECK(tree.search(cilantro::Vector3f(0.1f, 0.1f, 0.4f), cilantro::KNNNeighborhoodSpecification<>(3)).size() == 3);
+    CHECK(tree.search(cilantro::Vector3f(0.1f, 0.1f, 0.4f),
+                      cilantro::KNNInRadiusNeighborhoodSpecification<float>(5, 0.5f)).size() == 2);
   }
   // ---- principal_component_analysis.cpp ----------------------------------------------------------------
   {

@@ -151,3 +151,116 @@ def test_kd_tree_example_known_answer(cb, ctx):
     idx, d2, cnt = cb.knn_radius(ctx, ref, q, 2, None, 1.001)
     assert cnt[0] == 2 and list(idx[0]) == [0, 3]
     assert np.allclose(d2[0], [0.18, 0.38], rtol=1e-6)
+
+
+def _check_radius(cb, ctx, orc, dst, qry, r2, T=None):
+    off, idx, d2 = cb.radius_search(ctx, cb.Cloud(ctx, dst), cb.Cloud(ctx, qry), r2, T=T)
+    qt = orc.transform_points(T, qry) if T is not None else qry
+    _, _, cnt = orc.BruteKnn(dst).neighborhoods(qt, 0, r2, stride=1)
+    oi, od, cnt = orc.BruteKnn(dst).neighborhoods(qt, 0, r2, stride=max(1, int(cnt.max())))
+    assert np.array_equal(np.diff(off), cnt.astype(np.int64))
+    for i in range(qry.shape[0]):  # ragged rows: compare the used prefix of the padded oracle rows
+        m = cnt[i]
+        assert np.array_equal(idx[off[i]:off[i + 1]], oi[i, :m])
+        assert np.array_equal(d2[off[i]:off[i + 1]].view(np.uint32), od[i, :m].view(np.uint32))
+    return off, idx, d2
+
+
+def test_radius_search_matches_oracle_bitexact(cb, ctx, orc):
+    rng = np.random.default_rng(17)
+    dst = rng.random((20000, 3), dtype=np.float32)
+    qry = np.vstack([rng.random((1500, 3), dtype=np.float32), rng.random((50, 3), dtype=np.float32) * 3 - 1]).astype(np.float32)
+    off, idx, d2 = _check_radius(cb, ctx, orc, dst, qry, 0.06**2)
+    assert off[-1] > 10 * qry.shape[0] and (np.diff(off) == 0).any()  # long lists and empty ones
+    T = synth.rigid_from_axis_angle([0.2, 1, -0.4], 0.3, [0.05, -0.02, 0.01]).astype(np.float32)
+    _check_radius(cb, ctx, orc, dst, qry[:400], 0.04**2, T=T)
+    # duplicated reference points: equal distances come out in ascending index
+    dup = np.vstack([dst[:3000], dst[:3000]]).astype(np.float32)
+    _check_radius(cb, ctx, orc, dup, qry[:300], 0.08**2)
+    # radius 0 / empty clouds
+    off, idx, d2 = cb.radius_search(ctx, cb.Cloud(ctx, dst), cb.Cloud(ctx, qry[:10]), 0.0)
+    assert off[-1] == 0 and idx.size == 0
+    off, idx, d2 = cb.radius_search(ctx, cb.Cloud(ctx, dst[:0]), cb.Cloud(ctx, qry[:10]), 1.0)
+    assert off[-1] == 0
+
+
+def test_radius_search_agrees_with_reference_nanoflann(cb, ctx, orc):
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(23)
+    dst = rng.random((15000, 3), dtype=np.float32)
+    qry = rng.random((800, 3), dtype=np.float32)
+    r2 = 0.05**2
+    off, idx, d2 = cb.radius_search(ctx, cb.Cloud(ctx, dst), cb.Cloud(ctx, qry), r2)
+    ref = orc.RefKnn(dst)
+    _, _, cnt = ref.neighborhoods(qry, 0, r2, stride=1)
+    ri, rd, cnt = ref.neighborhoods(qry, 0, r2, stride=int(cnt.max()))
+    assert np.array_equal(np.diff(off), cnt.astype(np.int64))
+    for i in range(qry.shape[0]):  # random data: no equal distances, so the order is unique
+        assert np.array_equal(idx[off[i]:off[i + 1]], ri[i, :cnt[i]])
+        assert np.array_equal(d2[off[i]:off[i + 1]].view(np.uint32), rd[i, :cnt[i]].view(np.uint32))
+
+
+def _hollow_sphere(n, seed=0, radius=0.45, noise=0.002):
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((n, 3))
+    g /= np.linalg.norm(g, axis=1, keepdims=True)
+    r = radius + noise * rng.standard_normal((n, 1))
+    return (0.5 + g * r).astype(np.float32)
+
+
+def test_far_queries_cross_empty_space_exactly_and_fast(cb, ctx, orc):
+    # The far-query path (far_sweep.cuh): queries at the centre of a hollow scan and far outside it would cost
+    # O(shells^3) row tests with the shell sweep alone; they must stay exact and finish quickly.
+    import time
+
+    dst = _hollow_sphere(1_000_000, seed=3)
+    rng = np.random.default_rng(4)
+    qry = np.vstack([
+        0.5 + 0.05 * rng.standard_normal((3000, 3)),          # deep inside the hollow
+        0.5 + 40.0 * rng.standard_normal((1000, 3)),          # far outside the bounding box
+        rng.random((1000, 3)),                                # anywhere in the box
+        dst[:500] + np.float32(1e-4),                         # on the surface
+    ]).astype(np.float32)
+    ref, q = cb.Cloud(ctx, dst), cb.Cloud(ctx, qry)
+    cb.knn1_radius(ctx, ref, q, None, FMAX)  # builds the indices
+    t0 = time.perf_counter()
+    idx, d2 = cb.knn1_radius(ctx, ref, q, None, FMAX)
+    dt = time.perf_counter() - t0
+    oi, od = orc.BruteKnn(dst).query(qry, FMAX)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+    assert dt < 5.0, f"unbounded 1-NN of {qry.shape[0]} far queries took {dt:.1f} s"
+    # k nearest of far queries (k-best sweep restarts on the block list too)
+    sub = qry[::10]
+    t0 = time.perf_counter()
+    kidx, kd2, cnt = cb.knn_radius(ctx, ref, cb.Cloud(ctx, sub), 10, None, FMAX)
+    dt = time.perf_counter() - t0
+    bi, bd, bc = orc.BruteKnn(dst).neighborhoods(sub, 10, FMAX)
+    assert np.array_equal(cnt, bc) and np.array_equal(kidx, bi)
+    assert np.array_equal(kd2.view(np.uint32), bd.view(np.uint32))
+    assert dt < 5.0, f"unbounded 10-NN of {sub.shape[0]} far queries took {dt:.1f} s"
+    # bounded searches of the same queries still report "nothing within the radius"
+    idx_b, d2_b = cb.knn1_radius(ctx, ref, q, None, 0.01**2)
+    oi_b, od_b = orc.BruteKnn(dst).query(qry, np.float32(0.01**2))
+    assert np.array_equal(idx_b, oi_b) and np.array_equal(d2_b.view(np.uint32), od_b.view(np.uint32))
+
+
+def test_normals_with_isolated_outliers(cb, ctx, orc):
+    # scanner outliers far from the surface ask for k neighbours across empty space
+    pts, _ = synth.surface_cloud(300_000, seed=8, noise=0.0005)
+    rng = np.random.default_rng(9)
+    outliers = (np.array([0.5, 0.5, 0.5]) + 3.0 * rng.standard_normal((25, 3))).astype(np.float32)
+    cloud = np.vstack([pts, outliers]).astype(np.float32)
+    got = cb.Cloud(ctx, cloud).estimate_normals(k=10, view_point=[0.5, 0.5, 10.0], want_cov=True)
+    # Neighbourhoods: the reference's nanoflann for the surface points; brute force (ascending (d2, index), the
+    # CUDA path's rule) for the outliers, whose ~10 nearest surface points are several units away and so tie in
+    # fp32 d2 — the one case where the reference's order is its kd-tree traversal order.
+    knn = orc.make_knn(cloud)
+    idx, d2, cnt = knn.neighborhoods(cloud, 10, orc.FLT_MAX)
+    bi, bd, bc = orc.BruteKnn(cloud).neighborhoods(outliers, 10, orc.FLT_MAX)
+    m = pts.shape[0]
+    assert np.array_equal(np.sort(d2[m:], axis=1).view(np.uint32), bd.view(np.uint32))  # same distances either way
+    idx[m:], cnt[m:] = bi, bc
+    want = orc.estimate_normals(cloud, knn, k=10, view_point=[0.5, 0.5, 10.0], neighbors=(idx, cnt))
+    assert np.array_equal(got["cov6"].view(np.uint32), want[2].view(np.uint32))
