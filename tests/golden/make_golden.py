@@ -48,6 +48,26 @@ def compute(orc, use_ref=False):
     T_h[0] = Tr.astype(np.float32)
     out["ransac_counts"] = [int(c) for c in orc.ransac_score(d, s, T_h, 0.01)]
     out["pca_eigenvalues"] = orc.pca(pts)["eigenvalues"].astype(np.float64).tolist()
+    # §8(f) rows: neighbourhoods (reference nanoflann when use_ref), normals, downsampling, engine lists
+    sp, _ = synth.surface_cloud(8000, seed=42, noise=0.001)
+    nk = orc.RefKnn(sp) if (use_ref and orc.have_ref()) else orc.BruteKnn(sp)
+    ni, nd, nc = nk.neighborhoods(sp, 9, np.float32(0.05**2))
+    out["nbr_idx_sha"], out["nbr_d2_sha"], out["nbr_cnt_sha"] = _sha(ni), _sha(nd), _sha(nc)
+    nrm_o, curv_o, cov_o, _ = orc.estimate_normals(sp, nk, k=9, radius2=np.float32(0.05**2), view_point=[0.5, 0.5, 5.0])
+    out["normals_cov_sha"] = _sha(cov_o)
+    out["normals_first"] = nrm_o[:4].astype(np.float64).reshape(-1).tolist()
+    out["curvature_first"] = curv_o[:4].astype(np.float64).tolist()
+    ri, rd, rc = nk.neighborhoods(sp[:200], 0, np.float32(0.03**2), stride=64)
+    out["radius_cnt_sha"], out["radius_d2_sha"] = _sha(rc), _sha(rd)
+    for order in (0, 1):
+        dp, dn, _ = orc.grid_downsample(sp, 0.04, normals=nrm_o, order=order)
+        out[f"downsample_order{order}_sha"] = _sha(dp) + _sha(np.nan_to_num(dn))
+    f, s_, v = orc.engine_correspondences(dst, src, T, bk, np.float32(0.02**2), search_dir="both",
+                                          require_reciprocal=True, inlier_fraction=0.8)
+    out["engine_both_recip_frac_sha"] = _sha(f) + _sha(s_) + _sha(v)
+    f, s_, v = orc.engine_correspondences(dst, src, T, bk, np.float32(0.02**2), search_dir="first_to_second",
+                                          one_to_one=True)
+    out["engine_f2s_1to1_sha"] = _sha(f) + _sha(s_) + _sha(v)
     return out
 
 
@@ -59,6 +79,8 @@ if __name__ == "__main__":
     b = compute(oracle, use_ref=False)
     assert g["knn_idx_sha"] == b["knn_idx_sha"] and g["knn_d2_sha"] == b["knn_d2_sha"], \
         "brute-force restatement disagrees with the reference nanoflann on the golden case"
+    for key in ("nbr_idx_sha", "nbr_d2_sha", "nbr_cnt_sha", "normals_cov_sha", "radius_cnt_sha", "radius_d2_sha"):
+        assert g[key] == b[key], f"{key}: brute-force neighbourhoods disagree with the reference nanoflann"
     with open(os.path.join(HERE, "oracle_golden.json"), "w") as f:
         json.dump(g, f, indent=1)
     print("wrote oracle_golden.json; kNN backend:", g["knn_backend"])

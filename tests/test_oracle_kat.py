@@ -146,3 +146,10 @@ def test_golden_fixtures(orc):
     assert now["ransac_counts"] == g["ransac_counts"]
     for key in ("icp_p2p_T", "icp_combined_T", "pca_eigenvalues"):
         assert np.allclose(now[key], g[key], rtol=0, atol=2e-6), key
+    # §8(f) rows: neighbourhood lists / covariances / downsampled clouds / engine lists are integer or
+    # bit-exact fp32 work — the brute-force restatement must reproduce the hashes made with the reference nanoflann
+    for key in ("nbr_idx_sha", "nbr_d2_sha", "nbr_cnt_sha", "normals_cov_sha", "radius_cnt_sha", "radius_d2_sha",
+                "downsample_order0_sha", "downsample_order1_sha", "engine_both_recip_frac_sha", "engine_f2s_1to1_sha"):
+        assert now[key] == g[key], key
+    for key in ("normals_first", "curvature_first"):
+        assert np.allclose(now[key], g[key], rtol=0, atol=2e-6), key
