@@ -41,6 +41,7 @@
 #include <vector>
 
 #include "../cilantro_b200.h"
+#include "b200_ply.hpp"
 
 namespace cilantro {
 
@@ -932,6 +933,44 @@ public:
 
 struct PointCloud3f {
   VectorSet3f points, normals, colors;
+  PointCloud3f() = default;
+  // PLY passthrough (utilities/point_cloud.hpp:118-121, :502-543; b200_ply.hpp)
+  explicit PointCloud3f(const std::string& file_name) { fromPLYFile(file_name); }
+  PointCloud3f& fromPLYFile(const std::string& file_name, bool /*preload*/ = true) {
+    std::vector<float> p, n, c;
+    b200::ply::read(file_name, p, n, c);
+    auto assign = [](VectorSet3f& dst, const std::vector<float>& src) {
+      dst.resize(3, src.size() / 3);
+      if (!src.empty()) std::memcpy(dst.data(), src.data(), src.size() * sizeof(float));
+    };
+    assign(points, p);
+    assign(normals, n);
+    assign(colors, c);
+    return *this;
+  }
+  const PointCloud3f& toPLYFile(const std::string& file_name, bool binary = true) const {
+    b200::ply::write(file_name, binary, size(), points.data(), hasNormals() ? normals.data() : nullptr,
+                     hasColors() ? colors.data() : nullptr);
+    return *this;
+  }
+  PointCloud3f& clear() {  // :131-136
+    points.resize(3, 0);
+    normals.resize(3, 0);
+    colors.resize(3, 0);
+    return *this;
+  }
+  PointCloud3f& append(const PointCloud3f& cloud) {  // :138-152
+    const size_t n0 = size(), n1 = cloud.size();
+    auto grow = [&](VectorSet3f& dst, const VectorSet3f& src) {
+      dst.resize(3, n0 + n1);
+      if (n1) std::memcpy(dst.data() + 3 * n0, src.data(), 3 * n1 * sizeof(float));
+    };
+    const bool keep_n = normals.cols() == n0 && cloud.hasNormals(), keep_c = colors.cols() == n0 && cloud.hasColors();
+    grow(points, cloud.points);
+    if (keep_n) grow(normals, cloud.normals);
+    if (keep_c) grow(colors, cloud.colors);
+    return *this;
+  }
   // utilities/point_cloud.hpp:246-290
   PointCloud3f& gridDownsample(float bin_size, size_t min_points_in_bin = 1, bool parallel = true) {
     PointCloud3f res = gridDownsampled(bin_size, min_points_in_bin, parallel);
