@@ -155,6 +155,7 @@ struct cb_icp {
   float* d_nn_d2 = nullptr;
   bool nn_valid = false;    // a search has run; T_search / max_d2_search describe it
   bool nn_stored = false;   // d_nn_pos / d_nn_d2 hold that search's per-query result
+  bool warm_ok = false;     // d_nn_pos holds the previous iteration's matches of THIS estimate() call
   float T_search[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
   float max_d2_search = 0.f;
   cb::EnginePairs pairs;    // correspondence list of the last iteration in a non-default engine mode
@@ -556,7 +557,10 @@ static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, 
   for (int r = 0; r < 3; r++) a->sm[r] = smt[r];
   // The per-query result is only written when something will read it back (inner Gauss-Newton
   // iterations >= 2, cb_icp_accumulate); cb_icp_correspondences re-runs the search otherwise.
-  a->nn_pos = store ? icp->d_nn_pos : nullptr;
+  // The match positions are always kept: they seed the next iteration's search (warm start, warp_search.cuh).
+  static const bool no_warm = getenv("CB_NO_WARM_START") != nullptr;  // A/B switch for measurements
+  a->warm_pos = (icp->warm_ok && !no_warm) ? icp->d_nn_pos : nullptr;
+  a->nn_pos = (store || !no_warm) ? icp->d_nn_pos : nullptr;
   a->nn_d2 = store ? icp->d_nn_d2 : nullptr;
   std::memcpy(icp->T_search, T, sizeof(icp->T_search));
   icp->max_d2_search = prm->max_d2;
@@ -604,6 +608,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
     kabsch_from_moments(sums, Titer);
     *n_corr = sums[0];
     icp->nn_valid = true;
+    icp->warm_ok = true;
     return CB_OK;
   }
   // combined / symmetric Gauss-Newton (transform_estimation.hpp:238-367 / :608-739)
@@ -631,6 +636,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
     if (search) {
       *n_corr = sums[0];
       icp->nn_valid = true;
+      icp->warm_ok = !engine;
     }
     const bool has_terms = sums[0] > 0.0 && (w_pt_on || w_pl_on);
     if (!has_terms || bail_no_normals) {
@@ -675,6 +681,7 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   float last_delta = INFINITY;
   double n_corr = 0;
   icp->nn_valid = false;
+  icp->warm_ok = false;
   icp->search_ms = 0;
   while (iters < max_iter) {  // icp_base.hpp:76-84
     if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));

@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
   int pos = -1;
   if (SEARCH) {
     // every lane of the warp takes part in the pooled search (inactive tail lanes contribute no work)
-    const Best best = warp_grid_nearest(a.dst, wsm[threadIdx.x >> 5], active, qx, qy, qz, a.max_d2);
+    const int warm = (a.warm_pos && active) ? a.warm_pos[i] : -1;
+    const Best best = warp_grid_nearest(a.dst, wsm[threadIdx.x >> 5], active, qx, qy, qz, a.max_d2, warm);
     if (active) {
       pos = (best.idx >= 0 && best.d2 < a.max_d2) ? best.pos : -1;
       if (a.nn_pos) a.nn_pos[i] = pos;

@@ -28,6 +28,7 @@ struct IcpArgs {
   float dm[3];   // dst_mean_
   float sm[3];   // transform_ * src_mean_
   // per-query results, indexed by position in the SORTED query cloud (nullable)
+  const int* warm_pos;  // previous iteration's nn_pos (same layout) or nullptr: seeds the search (warp_search.cuh)
   int* nn_pos;    // position of the match in the sorted dst cloud, -1 = none
   float* nn_d2;   // its squared distance
   // per-query results in ORIGINAL query order (kModeKnn; nullable)

@@ -69,9 +69,11 @@ __constant__ signed char kRowDz[9] = {0, 0, 0, -1, 1, -1, -1, 1, 1};
 // kExact = true resolves exact ties on the original index inside the loop. kExact = false (the fast
 // pass) keeps the first strictly smaller candidate and only RECORDS that a bit-equal distance was
 // seen; grid_nearest() then repeats the search with kExact = true for that (very rare) query.
+// skip_pos (fast pass only): the position of a point that is ALREADY the running best (a warm start from the
+// previous ICP iteration, or the merged best of the warp-pooled search) — meeting it again is not a tie.
 template <bool kExact>
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint32_t b, uint32_t e, float qx,
-                                           float qy, float qz, Best& best) {
+                                           float qy, float qz, Best& best, int skip_pos = -1) {
   if (kExact) {
 #pragma unroll 2
     for (uint32_t j = b; j < e; ++j) {
@@ -101,7 +103,7 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, uint3
       if (r < best.d2) {
         best.d2 = r;
         best.pos = (int)j;
-      } else if (r == best.d2) {
+      } else if (r == best.d2 && (int)j != skip_pos) {
         best.tie = true;
       }
     };

@@ -38,8 +38,12 @@ __device__ __forceinline__ unsigned long long pack_key(float d2, unsigned int po
 }
 
 // All 32 lanes of the warp must call this (inactive lanes pass active = false).
+// warm_pos >= 0: sorted position of a point known to be close (the query's match in the previous ICP
+// iteration). Its exact distance under the current transform seeds the running best, so most of the 10
+// residual regions are pruned before they are queued; the result is unchanged (the seed is a real candidate
+// with its exact d2, and a bit-equal distance elsewhere still raises the tie flag).
 __device__ __forceinline__ Best warp_grid_nearest(const GridView& g, WarpSearchSmem& sm, bool active, float qx, float qy,
-                                                  float qz, float max_d2) {
+                                                  float qz, float max_d2, int warm_pos = -1) {
   const unsigned int lane = threadIdx.x & 31;
   const unsigned int lt_mask = (1u << lane) - 1u;
   Best best;
@@ -54,6 +58,17 @@ __device__ __forceinline__ Best warp_grid_nearest(const GridView& g, WarpSearchS
   const bool inside = active && g.n > 0 && cx >= 0 && cx < g.nx && cy >= 0 && cy < g.ny && cz >= 0 && cz < g.nz;
   bool slow = active && g.n > 0 && !inside;  // outside the grid: per-lane exact search at the end
 
+  if (inside && warm_pos >= 0) {
+    const float4 p = __ldg(g.pts + warm_pos);
+    const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+    float r = __fmul_rn(dx, dx);
+    r = __fadd_rn(r, __fmul_rn(dy, dy));
+    r = __fadd_rn(r, __fmul_rn(dz, dz));
+    if (r < max_d2) {
+      best.d2 = r;
+      best.pos = warm_pos;
+    }
+  }
   if (lane == 0) sm.tie_mask = 0u;
   sm.q[lane] = make_float4(qx, qy, qz, 0.f);
   sm.key[lane] = pack_key(max_d2, 0xffffffffu);
@@ -68,7 +83,7 @@ __device__ __forceinline__ Best warp_grid_nearest(const GridView& g, WarpSearchS
       s1 = __ldg(g.cell_start + cbase + cx);
       s2 = __ldg(g.cell_start + cbase + cx + 1);
     }
-    if (inside) scan_range<false>(g.pts, s1, s2, qx, qy, qz, best);
+    if (inside) scan_range<false>(g.pts, s1, s2, qx, qy, qz, best, best.pos);
     // lower bounds (cells, margin applied) of the 10 residual regions
     const float gxl = slab_gap(fx, cx, cx - 1), gxr = slab_gap(fx, cx, cx + 1);
     const float gym = slab_gap(fy, cy, cy - 1), gyp = slab_gap(fy, cy, cy + 1);
@@ -120,7 +135,7 @@ __device__ __forceinline__ Best warp_grid_nearest(const GridView& g, WarpSearchS
     loc.idx = -1;
     loc.pos = -1;
     loc.tie = false;
-    scan_range<false>(g.pts, b, e, q.x, q.y, q.z, loc);
+    scan_range<false>(g.pts, b, e, q.x, q.y, q.z, loc, (int)(unsigned int)(cur & 0xffffffffull));
     if (loc.pos >= 0) {
       const unsigned long long key = pack_key(loc.d2, (unsigned int)loc.pos);
       const unsigned long long old = atomicMin(&sm.key[ql], key);
