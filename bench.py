@@ -262,8 +262,14 @@ def run_ours(args, w):
     # the same K iterations again with the events around the search kernel only (timing=2): the
     # kernel's average duration for the roofline (one bracket per iteration at a time, see cb_icp_params)
     resk = icp.estimate(max_iter=args.steps, flush_l2=not args.no_flush, timing=2, **kw)
-    if cdist.max_over_ranks(wall) < 0.5:
-        icp.estimate(max_iter=max(args.steps, 50), flush_l2=False, timing=0, **kw)
+    # nvidia-smi needs ~0.1 s before its first sample and the legs above take milliseconds: keep the same
+    # kernel running until rank 0 holds at least 3 samples taken under this load (or 3 s have passed)
+    t_load = time.perf_counter()
+    while True:
+        need = 1.0 if (rank == 0 and len(sampler.lines) < 3 and time.perf_counter() - t_load < 3.0) else 0.0
+        if cdist.max_over_ranks(need) == 0.0:
+            break
+        icp.estimate(max_iter=max(args.steps, 200), flush_l2=False, timing=0, **kw)
     if rank == 0:
         clocks = sampler.stop()
     assert res["iterations"] == args.steps
@@ -380,7 +386,13 @@ def main():
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         return run_reference(args, w)
-    return run_ours(args, w)
+    try:
+        return run_ours(args, w)
+    finally:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

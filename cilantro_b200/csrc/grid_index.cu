@@ -59,12 +59,24 @@ __global__ void bbox_kernel(const float* __restrict__ raw, size_t n, int* bb) {
       mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
     }
   }
+  // warp results -> shared memory -> 6 atomics per block (one per warp was ~60 k contended atomics at 1 M)
+  __shared__ float s_mn[kThreads / 32][3], s_mx[kThreads / 32][3];
   if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-      atomicMin(bb + a, float_to_ordered(mn[a]));
-      atomicMax(bb + 3 + a, float_to_ordered(mx[a]));
+      s_mn[threadIdx.x >> 5][a] = mn[a];
+      s_mx[threadIdx.x >> 5][a] = mx[a];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    float lo = s_mn[0][threadIdx.x], hi = s_mx[0][threadIdx.x];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+      lo = fminf(lo, s_mn[w][threadIdx.x]);
+      hi = fmaxf(hi, s_mx[w][threadIdx.x]);
+    }
+    atomicMin(bb + threadIdx.x, float_to_ordered(lo));
+    atomicMax(bb + 3 + threadIdx.x, float_to_ordered(hi));
   }
 }
 
@@ -274,22 +286,31 @@ __global__ void gather_kernel(const float* __restrict__ raw, const float* __rest
 // points per coarse block (kBlockCells^3 cells): 64 row ranges of the final cell_start table
 __global__ void block_count_kernel(const uint32_t* __restrict__ cell_start, int nx, int ny, int nz, int bx, int by,
                                    int bz, uint32_t* __restrict__ cnt, uint32_t* __restrict__ flag) {
+  // one warp per coarse block: lane l takes rows l and l + 32 of the block's 8 x 8 (y, z) rows
   const size_t nb = (size_t)bx * by * bz;
-  for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b <= nb; b += (size_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t b = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5; b <= nb; b += warps) {
     if (b == nb) {
-      flag[b] = 0u;
+      if (lane == 0) flag[b] = 0u;
       continue;
     }
     const int X = (int)(b % bx), Y = (int)((b / bx) % by), Z = (int)(b / ((size_t)bx * by));
     const int x0 = X * kBlockCells, x1 = min(x0 + kBlockCells, nx);
     uint32_t c = 0;
-    for (int z = Z * kBlockCells; z < min((Z + 1) * kBlockCells, nz); ++z)
-      for (int y = Y * kBlockCells; y < min((Y + 1) * kBlockCells, ny); ++y) {
+#pragma unroll
+    for (int r = lane; r < kBlockCells * kBlockCells; r += 32) {
+      const int y = Y * kBlockCells + (r % kBlockCells), z = Z * kBlockCells + (r / kBlockCells);
+      if (y < ny && z < nz) {
         const size_t base = ((size_t)z * ny + y) * nx;
         c += cell_start[base + x1] - cell_start[base + x0];
       }
-    cnt[b] = c;
-    flag[b] = c > 0 ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) {
+      cnt[b] = c;
+      flag[b] = c > 0 ? 1u : 0u;
+    }
   }
 }
 
@@ -468,17 +489,16 @@ int ensure_index(cb_cloud* c) {
     uint32_t* d_cnt = nullptr;
     CB_CUDA(cudaMallocAsync(&d_cnt, (2 * nb + 2) * sizeof(uint32_t), ctx->stream));
     uint32_t* d_flag = d_cnt + nb;  // nb + 2 entries
-    block_count_kernel<<<grid_blocks(ctx, nb), kThreads, 0, ctx->stream>>>(d_hist, gp.nx, gp.ny, gp.nz, bx, by, bz,
+    block_count_kernel<<<grid_blocks(ctx, (nb + 1) * 32), kThreads, 0, ctx->stream>>>(d_hist, gp.nx, gp.ny, gp.nz, bx, by, bz,
                                                                          d_cnt, d_flag);
     CB_TRY(exclusive_scan_u32(ctx, d_flag, nb + 1, 0u));
-    uint32_t nblocks = 0;
-    CB_CUDA(cudaMemcpyAsync(&nblocks, d_flag + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(cudaStreamSynchronize(ctx->stream));
-    CB_CUDA(cudaMallocAsync(&c->d_blocks, std::max<size_t>(nblocks, 1) * sizeof(uint4), ctx->stream));
+    // at most min(nb, n) blocks are non-empty: sized without waiting for the count, which is read back at
+    // the final synchronise below
+    CB_CUDA(cudaMallocAsync(&c->d_blocks, std::max<size_t>(std::min(nb, n), 1) * sizeof(uint4), ctx->stream));
     block_emit_kernel<<<grid_blocks(ctx, nb), kThreads, 0, ctx->stream>>>(d_cnt, d_flag, bx, by, bz, c->d_blocks);
     ctx->launches += 2;
     CB_CUDA(cudaGetLastError());
-    c->nblocks = nblocks;
+    CB_CUDA(cudaMemcpyAsync(&c->nblocks, d_flag + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(cudaFreeAsync(d_cnt, ctx->stream));
   }
   CB_CUDA(cudaFreeAsync(d_cell_id, ctx->stream));
