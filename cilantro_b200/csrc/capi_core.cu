@@ -132,14 +132,7 @@ int fetch_result(cb_context* ctx, int count, bool allreduce, double* out) {
   return CB_OK;
 }
 
-static Rigid to_rigid(const float* T12) {
-  Rigid r;
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) r.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
-    r.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
-  }
-  return r;
-}
+static Rigid to_rigid(const float* T12) { return rigid_from_t12(T12); }
 
 }  // namespace cb
 

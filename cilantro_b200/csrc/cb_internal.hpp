@@ -164,6 +164,33 @@ int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out);
 bool arm_exchange(cb_context* ctx, Exchange* ex);
 int wait_exchange(cb_context* ctx, int count, double* out);
 
+// Scoped stream-ordered scratch: everything alloc()ed is cudaFreeAsync()ed on the context's stream when the
+// object goes out of scope, unless release()d to the caller.
+struct DeviceScope {
+  cb_context* ctx;
+  std::vector<void*> ptrs;
+  explicit DeviceScope(cb_context* c) : ctx(c) {}
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+  template <class T>
+  int alloc(T** p, size_t count) {
+    *p = nullptr;
+    CB_CUDA(cudaMallocAsync((void**)p, (count ? count : 1) * sizeof(T), ctx->stream));
+    ptrs.push_back(*p);
+    return CB_OK;
+  }
+  void release(void* p) {
+    for (size_t i = 0; i < ptrs.size(); i++)
+      if (ptrs[i] == p) {
+        ptrs.erase(ptrs.begin() + (long)i);
+        return;
+      }
+  }
+  ~DeviceScope() {
+    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
+  }
+};
+
 // Correspondence list of the non-default engine modes (icp_engine.cu): device arrays of `count` pairs in
 // the reference's list order, ORIGINAL indices (first = dst point, second = src point).
 struct EnginePairs {

@@ -174,22 +174,7 @@ int bits_for(uint64_t count) {  // bits needed to represent values 0 .. count-1
   return std::max(b, 1);
 }
 
-struct DeviceBufs {  // frees everything it owns on scope exit (stream-ordered)
-  cb_context* ctx;
-  std::vector<void*> ptrs;
-  explicit DeviceBufs(cb_context* c) : ctx(c) {}
-  template <class T>
-  int alloc(T** p, size_t count) {
-    *p = nullptr;
-    CB_CUDA(cudaMallocAsync((void**)p, std::max<size_t>(count, 1) * sizeof(T), ctx->stream));
-    ptrs.push_back(*p);
-    return CB_OK;
-  }
-  void release(void* p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
-  ~DeviceBufs() {
-    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
-  }
-};
+using DeviceBufs = DeviceScope;  // scoped stream-ordered allocations (cb_internal.hpp)
 
 // Device-side core: inputs are packed xyz arrays in device memory; outputs are freshly allocated device
 // arrays of *out_n entries (caller frees with cudaFreeAsync on ctx->stream; nullptr when *out_n == 0).

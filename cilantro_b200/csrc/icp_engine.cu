@@ -35,22 +35,7 @@ inline int blocks_for(const cb_context* ctx, size_t n) {
   return (int)std::max<size_t>(1, std::min<size_t>((n + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 16));
 }
 
-struct Dev {  // scoped stream-ordered allocations
-  cb_context* ctx;
-  std::vector<void*> ptrs;
-  explicit Dev(cb_context* c) : ctx(c) {}
-  template <class T>
-  int alloc(T** p, size_t count) {
-    *p = nullptr;
-    CB_CUDA(cudaMallocAsync((void**)p, std::max<size_t>(count, 1) * sizeof(T), ctx->stream));
-    ptrs.push_back(*p);
-    return CB_OK;
-  }
-  void release(void* p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
-  ~Dev() {
-    for (void* p : ptrs) cudaFreeAsync(p, ctx->stream);
-  }
-};
+using Dev = DeviceScope;  // scoped stream-ordered allocations (cb_internal.hpp)
 
 // Candidate c of the pre-filter list: c < n_a -> the S2F pair of src point c (when s2f_idx != nullptr),
 // else the F2S pair of dst point c - n_a. Validity includes the union / intersection rules of BOTH.
@@ -197,14 +182,7 @@ int read_u32(cb_context* ctx, const uint32_t* d, uint32_t* out) {
   return CB_OK;
 }
 
-Rigid rigid_of(const float* T12) {
-  Rigid r;
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) r.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
-    r.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
-  }
-  return r;
-}
+Rigid rigid_of(const float* T12) { return rigid_from_t12(T12); }
 
 // ---- accumulation over the list ---------------------------------------------------------------------
 template <int MODE>

@@ -84,11 +84,7 @@ extern "C" int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_clou
   CB_TRY(ensure_index(const_cast<cb_cloud*>(qry)));
   const size_t nq = qry->n;
   if (nq == 0) return CB_OK;
-  Rigid T;
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) T.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
-    T.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
-  }
+  const Rigid T = rigid_from_t12(T12);
   int* d_idx = nullptr;
   float* d_d2 = nullptr;
   uint32_t* d_cnt = nullptr;
@@ -212,11 +208,7 @@ extern "C" int cb_radius_search(cb_context* ctx, const cb_cloud* ref, const cb_c
   *total = 0;
   offsets[0] = 0;
   if (nq == 0) return CB_OK;
-  Rigid T;
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) T.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
-    T.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
-  }
+  const Rigid T = rigid_from_t12(T12);
   uint32_t* d_off = nullptr;
   CB_CUDA(cudaMallocAsync(&d_off, (nq + 2) * sizeof(uint32_t), ctx->stream));
   CB_CUDA(cudaMemsetAsync(d_off, 0, (nq + 2) * sizeof(uint32_t), ctx->stream));

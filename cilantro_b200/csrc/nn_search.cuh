@@ -25,6 +25,16 @@ struct Rigid {
   float t[3];
 };
 
+// float[12] row-major [R | t] of the C ABI -> Rigid (nullptr = identity)
+inline Rigid rigid_from_t12(const float* T12) {
+  Rigid r;
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) r.r[i * 3 + j] = T12 ? T12[i * 4 + j] : (i == j ? 1.f : 0.f);
+    r.t[i] = T12 ? T12[i * 4 + 3] : 0.f;
+  }
+  return r;
+}
+
 __device__ __forceinline__ float sum3(float a0, float a1, float a2) { return __fadd_rn(a0, __fadd_rn(a1, a2)); }
 
 __device__ __forceinline__ void apply_rigid(const Rigid& T, float x, float y, float z, float& qx, float& qy,
