@@ -53,15 +53,19 @@ __device__ __forceinline__ float far_radius_bound(const GridView& g, float fx, f
   float r = inf;
   for (uint32_t i = 0; i < g.nblocks; ++i) r = fminf(r, block_bounds(__ldg(g.blocks + i), fx, fy, fz, g.nx, g.ny, g.nz).hi2);
   if (k_needed > 1) {
-    for (;;) {  // grow until enough points are certainly inside (at most ~log2(extent^2) rounds)
+    // grow until enough points are certainly inside: at most ~log2(extent^2) rounds for a finite query; the
+    // round cap makes a NaN / Inf query (all comparisons false) fall back to "no bound" instead of spinning
+    bool enough = false;
+    for (int round = 0; round < 96 && !enough; ++round) {
       uint32_t c = 0;
       for (uint32_t i = 0; i < g.nblocks; ++i) {
         const uint4 b = __ldg(g.blocks + i);
         if (block_bounds(b, fx, fy, fz, g.nx, g.ny, g.nz).hi2 <= r) c += b.w;
       }
-      if (c >= k_needed) break;
-      r *= 2.f;
+      enough = c >= k_needed;
+      if (!enough) r *= 2.f;
     }
+    if (!enough) return inf;
   }
   return r * h_up2;
 }

@@ -16,6 +16,8 @@ template <class BoundFn, class ScanFn, class ResetFn>
 __device__ __forceinline__ void grid_sweep(const GridView& g, float qx, float qy, float qz, BoundFn bound,
                                            ScanFn scan, ResetFn reset, uint32_t k_needed) {
   if (g.n == 0) return;
+  // a NaN / Inf query is at no finite distance from anything: no candidate can pass d2 < bound
+  if (!(fabsf(qx) + fabsf(qy) + fabsf(qz) < 3.0e38f)) return;
   const float fx = cell_coord(qx, g.ox, g.inv_h), fy = cell_coord(qy, g.oy, g.inv_h),
               fz = cell_coord(qz, g.oz, g.inv_h);
   const int cx = (int)floorf(fx), cy = (int)floorf(fy), cz = (int)floorf(fz);

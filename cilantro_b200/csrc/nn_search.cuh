@@ -156,6 +156,8 @@ __device__ __forceinline__ Best grid_nearest_impl(const GridView& g, float qx, f
   best.pos = -1;
   best.tie = false;
   if (g.n == 0) return best;
+  // a NaN / Inf query is at no finite distance from anything: no candidate can pass d2 < best
+  if (!(fabsf(qx) + fabsf(qy) + fabsf(qz) < 3.0e38f)) return best;
 
   const float fx = cell_coord(qx, g.ox, g.inv_h);
   const float fy = cell_coord(qy, g.oy, g.inv_h);

@@ -272,3 +272,37 @@ def test_normals_with_isolated_outliers(cb, ctx, orc):
     assert tied.sum() < 20
     assert np.array_equal(got["cov6"][~tied].view(np.uint32), want[2][~tied].view(np.uint32))
     assert np.isfinite(got["cov6"][tied]).all()  # a legitimate alternative neighbourhood: nothing more to compare
+
+
+def test_nan_and_inf_points_are_inert(cb, ctx, orc):
+    # NaN / Inf coordinates (organised depth clouds carry them): such a query finds nothing, such a reference
+    # point is never found, and nothing hangs — in every search flavour and in normal estimation.
+    rng = np.random.default_rng(31)
+    dst = rng.random((20000, 3), dtype=np.float32)
+    dst[[5, 77, 1234]] = np.nan
+    dst[[9, 500]] = np.inf
+    qry = rng.random((3000, 3), dtype=np.float32)
+    qry[[0, 10]] = np.nan
+    qry[[1, 11], 1] = np.inf
+    qry[2, 2] = -np.inf
+    ref, q = cb.Cloud(ctx, dst), cb.Cloud(ctx, qry)
+    brute = orc.BruteKnn(dst)
+    for max_d2 in (np.float32(0.05**2), FMAX):
+        idx, d2 = cb.knn1_radius(ctx, ref, q, None, max_d2)
+        oi, od = brute.query(qry, max_d2)
+        assert np.array_equal(idx, oi) and np.array_equal(d2.view(np.uint32), od.view(np.uint32))
+        assert np.all(idx[[0, 1, 2, 10, 11]] == -1)
+        kidx, kd2, cnt = cb.knn_radius(ctx, ref, q, 6, None, max_d2)
+        bi, bd, bc = brute.neighborhoods(qry, 6, max_d2)
+        assert np.array_equal(cnt, bc) and np.array_equal(kidx, bi) and np.array_equal(kd2.view(np.uint32), bd.view(np.uint32))
+    off, ridx, rd2 = cb.radius_search(ctx, ref, q, 0.04**2)
+    _, _, bc = brute.neighborhoods(qry, 0, np.float32(0.04**2), stride=1)
+    assert np.array_equal(np.diff(off), bc.astype(np.int64)) and bc[[0, 1, 2, 10, 11]].sum() == 0
+    bad = np.array([5, 9, 77, 500, 1234])
+    assert not np.isin(idx, bad).any() and not np.isin(ridx, bad).any()
+    # normals of the cloud with its own bad points as queries: NaN rows there, exact elsewhere
+    got = ref.estimate_normals(k=8, view_point=[0.5, 0.5, 5.0], want_cov=True)
+    want = orc.estimate_normals(dst, brute, k=8, view_point=[0.5, 0.5, 5.0])
+    assert np.isnan(got["normals"][bad]).all() and np.isnan(got["curvature"][bad]).all()
+    good = np.setdiff1d(np.arange(dst.shape[0]), bad)
+    assert np.array_equal(got["cov6"][good].view(np.uint32), want[2][good].view(np.uint32))
