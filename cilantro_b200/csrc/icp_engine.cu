@@ -99,16 +99,18 @@ __global__ void candidate_compact_kernel(const Candidates c, uint32_t total, con
 
 enum KeyKind : int { kKeyLex = 0, kKeyValuePos = 1, kKeyFirstValue = 2, kKeySecondValue = 3 };
 
+// key = (high field << low_bits) | low field, packed tightly so that the radix sort only runs the passes the
+// value ranges need (low_bits = width of the low field: index bits, value bits or position bits)
 __global__ void pair_key_kernel(const uint32_t* __restrict__ first, const uint32_t* __restrict__ second,
-                                const float* __restrict__ d2, uint32_t m, int kind, uint64_t* __restrict__ keys,
-                                uint32_t* __restrict__ vals) {
+                                const float* __restrict__ d2, uint32_t m, int kind, int low_bits,
+                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
     const uint64_t v = (uint64_t)__float_as_uint(d2[p]);  // d2 >= 0: the bit pattern is monotone
     uint64_t k;
-    if (kind == kKeyLex) k = ((uint64_t)first[p] << 32) | second[p];
-    else if (kind == kKeyValuePos) k = (v << 32) | p;
-    else if (kind == kKeyFirstValue) k = ((uint64_t)first[p] << 32) | v;
-    else k = ((uint64_t)second[p] << 32) | v;
+    if (kind == kKeyLex) k = ((uint64_t)first[p] << low_bits) | second[p];
+    else if (kind == kKeyValuePos) k = (v << low_bits) | p;
+    else if (kind == kKeyFirstValue) k = ((uint64_t)first[p] << low_bits) | v;
+    else k = ((uint64_t)second[p] << low_bits) | v;
     keys[p] = k;
     vals[p] = p;
   }
@@ -156,12 +158,13 @@ struct PairBufs {
   int cur = 0;
 };
 
-int sort_pairs(cb_context* ctx, PairBufs& b, uint32_t m, int kind, int bits) {
+int sort_pairs(cb_context* ctx, PairBufs& b, uint32_t m, int kind, int high_bits, int low_bits) {
   if (m <= 1) return CB_OK;
   const int nb = blocks_for(ctx, m);
-  pair_key_kernel<<<nb, kThreads, 0, ctx->stream>>>(b.f[b.cur], b.s[b.cur], b.d[b.cur], m, kind, b.keys[0], b.vals[0]);
+  pair_key_kernel<<<nb, kThreads, 0, ctx->stream>>>(b.f[b.cur], b.s[b.cur], b.d[b.cur], m, kind, low_bits, b.keys[0],
+                                                   b.vals[0]);
   ctx->launches += 1;
-  CB_TRY(radix_sort_pairs_u64(ctx, b.keys[0], b.vals[0], b.keys[1], b.vals[1], m, bits));
+  CB_TRY(radix_sort_pairs_u64(ctx, b.keys[0], b.vals[0], b.keys[1], b.vals[1], m, high_bits + low_bits));
   pair_gather_kernel<<<nb, kThreads, 0, ctx->stream>>>(b.vals[0], m, b.f[b.cur], b.s[b.cur], b.d[b.cur],
                                                       b.f[b.cur ^ 1], b.s[b.cur ^ 1], b.d[b.cur ^ 1]);
   ctx->launches += 1;
@@ -325,18 +328,22 @@ int engine_find_pairs(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src,
   uint32_t m = 0;
   CB_TRY(read_u32(ctx, b.flags + total, &m));
   const int idx_bits = bits_of(std::max(n_src, n_dst));
-  if (c.both) CB_TRY(sort_pairs(ctx, b, m, kKeyLex, 64));  // lexicographic (first, second)
+  // every kept value is < max_d2, and non-negative floats order like their bit patterns
+  uint32_t max_bits_pattern;
+  std::memcpy(&max_bits_pattern, &prm->max_d2, sizeof(uint32_t));
+  const int val_bits = bits_of(max_bits_pattern);
+  if (c.both) CB_TRY(sort_pairs(ctx, b, m, kKeyLex, idx_bits, idx_bits));  // lexicographic (first, second)
   // filterCorrespondencesFraction
   const double fr = prm->inlier_fraction;
   if (fr > 0.0 && fr < 1.0 && m > 0) {
-    CB_TRY(sort_pairs(ctx, b, m, kKeyValuePos, 64));
+    CB_TRY(sort_pairs(ctx, b, m, kKeyValuePos, val_bits, bits_of(m)));
     const long long keep = std::llround(fr * (double)m);
     m = (uint32_t)std::min<long long>(std::max<long long>(keep, 0), (long long)m);
   }
   // filterCorrespondencesOneToOne (returns early on an empty list; BOTH: no-op)
   if (prm->one_to_one && m > 0 && prm->search_dir != CB_BOTH) {
     const bool by_first = prm->search_dir == CB_SECOND_TO_FIRST;
-    CB_TRY(sort_pairs(ctx, b, m, by_first ? kKeyFirstValue : kKeySecondValue, 32 + idx_bits));
+    CB_TRY(sort_pairs(ctx, b, m, by_first ? kKeyFirstValue : kKeySecondValue, idx_bits, val_bits));
     const uint32_t* index = by_first ? b.f[b.cur] : b.s[b.cur];
     const int mb = blocks_for(ctx, m);
     group_head_flag_kernel<<<mb, kThreads, 0, ctx->stream>>>(index, m, b.flags);
