@@ -76,8 +76,16 @@ def ransac(args, n=5_000_000, batch=1000):
     capi, ctx = _ctx()
     dst, src, T_ref, inl = synth.ransac_pairs(n, 0.3, seed=1)
     d_dst, d_src = capi.Cloud(ctx, dst), capi.Cloud(ctx, src)
-    samples = oracle.ransac_samples(n, 3, batch, seed=7)
-    T_h = oracle.ransac_fit_samples(dst, src, samples)
+    # hypotheses: the generating pose plus random rigid perturbations of it (inputs of the measured scoring call;
+    # the oracle below only scores a few of them as the CPU baseline / checker)
+    rng = np.random.default_rng(7)
+    T_h = np.empty((batch, 3, 4), np.float32)
+    T_h[0] = T_ref.astype(np.float32)
+    R0, t0_ = np.asarray(T_ref)[:, :3], np.asarray(T_ref)[:, 3]
+    for h in range(1, batch):
+        dT = np.asarray(synth.rigid_from_axis_angle(rng.standard_normal(3), 0.05 * rng.standard_normal(),
+                                                    0.05 * rng.standard_normal(3)))
+        T_h[h] = np.hstack([dT[:, :3] @ R0, (dT[:, :3] @ t0_ + dT[:, 3])[:, None]]).astype(np.float32)
     for _ in range(max(args.warmup, 1)):
         capi.ransac_score(ctx, d_dst, d_src, T_h[:64], 0.01)
     l0 = ctx.kernel_launches()
