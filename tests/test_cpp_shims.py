@@ -31,3 +31,19 @@ def test_reference_examples_through_cpp_shims(cb, tmp_path):
     print(out.stdout)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "all C++ shim checks passed" in out.stdout
+
+
+def test_example_program_compiles():
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", INC,
+                           os.path.join(ROOT, "examples", "register_clouds.cpp")], env=_env())
+
+
+@pytest.mark.gpu
+def test_example_program_registers_a_synthetic_pair(cb, tmp_path):
+    exe = str(tmp_path / "register_clouds")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I", INC, os.path.join(ROOT, "examples", "register_clouds.cpp"),
+                           "-o", exe, "-L", LIBDIR, "-lcilantro_b200", f"-Wl,-rpath,{LIBDIR}"], env=_env())
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    print(out.stdout)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "wrote registered.ply" in out.stdout and os.path.exists(tmp_path / "registered.ply")
