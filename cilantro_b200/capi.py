@@ -79,6 +79,7 @@ EXPORTED = [
     "cb_context_create", "cb_context_destroy", "cb_context_synchronize", "cb_context_device_info",
     "cb_context_kernel_launches", "cb_context_flush_l2",
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
+    "cb_comm_ipc_detach",
     "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
     "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
     "cb_knn1_radius", "cb_knn_radius", "cb_radius_search", "cb_find_correspondences",
@@ -187,6 +188,9 @@ class Context:
     def ipc_attach(self, handles: bytes):
         buf = C.create_string_buffer(handles, len(handles))
         _check(lib().cb_comm_ipc_attach(self.h, buf))
+
+    def ipc_detach(self):
+        _check(lib().cb_comm_ipc_detach(self.h))
 
     def comm_info(self):
         r, w = C.c_int(), C.c_int()

@@ -310,6 +310,12 @@ int cb_comm_ipc_attach(cb_context* ctx, const void* handles) {
   return CB_OK;
 }
 
+int cb_comm_ipc_detach(cb_context* ctx) {
+  CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
+  if (ctx->world > 1) ctx->ex_ready = false;  // every later pass reduces through NCCL; the mappings stay harmlessly open
+  return CB_OK;
+}
+
 int cb_context_comm_info(cb_context* ctx, int* rank, int* world) {
   CB_CHECK(ctx, CB_ERR_INVALID, "ctx is null");
   if (rank) *rank = ctx->rank;

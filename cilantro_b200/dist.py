@@ -67,12 +67,20 @@ def attach_comm(ctx):
         dist.all_gather_object(handles, ctx.ipc_handle())
         ok = 1
         try:
+            if os.environ.get("CB_TEST_IPC_FAIL_RANK") == str(rank):  # test hook: pretend this rank cannot map its peers
+                raise capi.CbError("simulated cudaIpcOpenMemHandle failure")
             ctx.ipc_attach(b"".join(handles))
         except capi.CbError:
             ok = 0
         if min_over_ranks(ok) == 0:
-            raise RuntimeError("fused exchange could not be mapped on every rank; set CB_NO_FUSED_EXCHANGE=1 "
-                               "to use the NCCL all-reduce path")
+            # no peer mapping somewhere (e.g. no P2P between two of the GPUs): every rank goes back to the NCCL
+            # all-reduce path, together
+            ctx.ipc_detach()
+            if rank == 0:
+                import sys
+
+                print("cilantro_b200: fused NVLink exchange unavailable on some rank, using ncclAllReduce",
+                      file=sys.stderr)
     dist.barrier()
     return rank, world
 

@@ -78,6 +78,9 @@ int cb_context_comm_info(cb_context* ctx, int* rank, int* world);
  * If mapping fails (no peer access) the call returns an error and the NCCL path stays active. */
 int cb_comm_ipc_handle(cb_context* ctx, void* out_64_bytes);
 int cb_comm_ipc_attach(cb_context* ctx, const void* handles_world_x_64_bytes);
+/* Back to the NCCL reduction on this rank. The launcher calls it on EVERY rank when cb_comm_ipc_attach failed
+ * on any of them (the ranks must agree on the path before the first pass). */
+int cb_comm_ipc_detach(cb_context* ctx);
 
 /* ---- device-resident point sets --------------------------------------------------------------
  * Replaces: PointFeaturesAdaptor<float,3> ctor (correspondence_search/
