@@ -191,6 +191,23 @@ struct DeviceScope {
   }
 };
 
+// A pair of CUDA events that is destroyed on every exit path.
+struct ScopedEvents {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ScopedEvents() = default;
+  ScopedEvents(const ScopedEvents&) = delete;
+  ScopedEvents& operator=(const ScopedEvents&) = delete;
+  int create() {
+    CB_CUDA(cudaEventCreate(&e0));
+    CB_CUDA(cudaEventCreate(&e1));
+    return CB_OK;
+  }
+  ~ScopedEvents() {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  }
+};
+
 // Correspondence list of the non-default engine modes (icp_engine.cu): device arrays of `count` pairs in
 // the reference's list order, ORIGINAL indices (first = dst point, second = src point).
 struct EnginePairs {

@@ -323,26 +323,23 @@ extern "C" int cb_cloud_grid_downsample(cb_context* ctx, const cb_cloud* cloud, 
   CB_CHECK(order == 0 || order == 1, CB_ERR_INVALID, "order must be 0 (bin order) or 1 (first occurrence)");
   CB_CUDA(cudaSetDevice(ctx->device));
   *out = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ScopedEvents ev;
   if (gpu_ms) {
     *gpu_ms = 0.f;
-    CB_CUDA(cudaEventCreate(&e0));
-    CB_CUDA(cudaEventCreate(&e1));
-    CB_CUDA(cudaEventRecord(e0, ctx->stream));
+    CB_TRY(ev.create());
+    CB_CUDA(cudaEventRecord(ev.e0, ctx->stream));
   }
   float *o_pts = nullptr, *o_nrm = nullptr;
   size_t m = 0;
   CB_TRY(downsample_device(ctx, cloud->d_raw, cloud->d_raw_nrm, nullptr, cloud->n, bin_size, min_points_in_bin, order,
                            &o_pts, &o_nrm, nullptr, &m));
-  if (gpu_ms) CB_CUDA(cudaEventRecord(e1, ctx->stream));
+  if (gpu_ms) CB_CUDA(cudaEventRecord(ev.e1, ctx->stream));
   const int rc = cb_cloud_create_from_device(ctx, o_pts, o_nrm, m, cloud->index_offset, out);
   if (o_pts) cudaFreeAsync(o_pts, ctx->stream);
   if (o_nrm) cudaFreeAsync(o_nrm, ctx->stream);
   if (gpu_ms) {
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
-    CB_CUDA(cudaEventElapsedTime(gpu_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CB_CUDA(cudaEventElapsedTime(gpu_ms, ev.e0, ev.e1));
   }
   return rc;
 }

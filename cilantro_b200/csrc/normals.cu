@@ -310,11 +310,10 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
   const float max_d2 = radius2 > 0.f ? radius2 : 3.402823466e38f;
   const GridView g = grid_view(cloud);
   const int blocks = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count * 8, (n + kBlock - 1) / kBlock));
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  ScopedEvents ev;
   if (gpu_ms) {
-    CB_CUDA(cudaEventCreate(&e0));
-    CB_CUDA(cudaEventCreate(&e1));
-    CB_CUDA(cudaEventRecord(e0, ctx->stream));
+    CB_TRY(ev.create());
+    CB_CUDA(cudaEventRecord(ev.e0, ctx->stream));
   }
   if (k == 0)
     normals_radius_kernel<<<blocks, kBlock, 0, ctx->stream>>>(g, max_d2, o);
@@ -325,7 +324,7 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
   else
     normals_knn_kernel<32><<<blocks, kBlock, 0, ctx->stream>>>(g, k, max_d2, o);
   ctx->launches += 1;
-  if (gpu_ms) CB_CUDA(cudaEventRecord(e1, ctx->stream));
+  if (gpu_ms) CB_CUDA(cudaEventRecord(ev.e1, ctx->stream));
   CB_CUDA(cudaGetLastError());
   if (normals)
     CB_CUDA(cudaMemcpyAsync(normals, cloud->d_raw_nrm, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -335,10 +334,6 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
   if (d_curv) CB_CUDA(cudaFreeAsync(d_curv, ctx->stream));
   if (d_cov) CB_CUDA(cudaFreeAsync(d_cov, ctx->stream));
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (gpu_ms) {
-    CB_CUDA(cudaEventElapsedTime(gpu_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-  }
+  if (gpu_ms) CB_CUDA(cudaEventElapsedTime(gpu_ms, ev.e0, ev.e1));
   return CB_OK;
 }
