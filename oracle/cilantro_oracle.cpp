@@ -14,7 +14,14 @@
 //     query (equal index, or bit-equal d2 on exact ties), see tests/test_oracle_knn.py;
 //   * the hand-derivable known answers of examples/kd_tree.cpp and
 //     examples/principal_component_analysis.cpp (tests/test_oracle_kat.py);
-//   * the self-checking recipe of examples/rigid_icp.cpp (estimate ~= tf_ref^-1).
+//   * the self-checking recipe of examples/rigid_icp.cpp (estimate ~= tf_ref^-1);
+//   * the callers either side of the path (normal estimation, voxel-grid downsampling, the correspondence
+//     engine's non-default modes): k-neighbourhoods and radius lists come from the reference nanoflann
+//     (tests/test_oracle_normals.py, tests/golden/make_golden.py refuse a brute-force / nanoflann mismatch);
+//     the per-neighbourhood covariance, the std::map grid accumulation and the sort / set_union /
+//     set_intersection filters are restated line by line with hand-derivable known answers
+//     (tests/test_oracle_normals.py, tests/test_oracle_downsample.py) and hashed into
+//     tests/golden/oracle_golden.json.
 // The Eigen-typed O(1) solves (JacobiSVD, LDLT, SelfAdjointEigenSolver) are "parity
 // unpinned": Eigen3 is an external, unversioned dependency (CMakeLists.txt:7) absent here.
 //
