@@ -80,7 +80,7 @@ EXPORTED = [
     "cb_context_kernel_launches", "cb_context_flush_l2",
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_comm_ipc_detach",
-    "cb_cloud_create", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
+    "cb_cloud_create", "cb_cloud_create_pair", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
     "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
     "cb_knn1_radius", "cb_knn_radius", "cb_radius_search", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
@@ -282,6 +282,17 @@ class Cloud:
         occ = C.c_double()
         _check(lib().cb_cloud_grid_info(self.h, C.byref(edge), dims, C.byref(occ)))
         return {"cell_edge": edge.value, "dims": list(dims), "mean_occupancy": occ.value}
+
+
+def cloud_pair(ctx, xyz_a, normals_a, xyz_b, normals_b, offset_a=0, offset_b=0):
+    """cb_cloud_create_pair: two indexed Clouds; the second upload overlaps the first grid build."""
+    xa, xb = _f32(xyz_a), _f32(xyz_b)
+    na = _f32(normals_a) if normals_a is not None else None
+    nb = _f32(normals_b) if normals_b is not None else None
+    ha, hb = C.c_void_p(), C.c_void_p()
+    _check(lib().cb_cloud_create_pair(ctx.h, _p(xa), _p(na), C.c_size_t(xa.shape[0]), C.c_uint64(offset_a), _p(xb), _p(nb),
+                                      C.c_size_t(xb.shape[0]), C.c_uint64(offset_b), C.byref(ha), C.byref(hb)))
+    return Cloud._wrap(ctx, ha), Cloud._wrap(ctx, hb)
 
 
 def radius_search(ctx, ref, qry, radius2, T=None):

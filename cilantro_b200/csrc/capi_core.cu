@@ -224,6 +224,7 @@ void cb_context_destroy(cb_context* ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -345,6 +346,66 @@ static int cloud_create_common(cb_context* ctx, const float* xyz, const float* n
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   *out = c;
+  return CB_OK;
+}
+
+// Two clouds at once (the constructor arguments of an ICP object): the host-to-device copy of the second runs on
+// a second stream while the grid index of the first is built, so its PCIe time disappears from the critical path
+// when the caller's buffers are pinned (pageable buffers make the copy synchronous: same result, no overlap).
+// Both clouds are indexed when the call returns and the caller's buffers may be released.
+int cb_cloud_create_pair(cb_context* ctx, const float* xyz_a, const float* normals_a, size_t n_a, uint64_t offset_a,
+                         const float* xyz_b, const float* normals_b, size_t n_b, uint64_t offset_b, cb_cloud** out_a,
+                         cb_cloud** out_b) {
+  CB_CHECK(ctx && out_a && out_b, CB_ERR_INVALID, "null argument");
+  CB_CHECK((n_a == 0 || xyz_a) && (n_b == 0 || xyz_b), CB_ERR_INVALID, "xyz is null");
+  CB_CHECK(n_a < (1ull << 31) && n_b < (1ull << 31), CB_ERR_INVALID, "point sets of >= 2^31 points are not supported");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  *out_a = *out_b = nullptr;
+  if (!ctx->copy_stream) CB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  ScopedEvents ev;
+  CB_TRY(ev.create());
+  cb_cloud* a = new cb_cloud;
+  cb_cloud* b = new cb_cloud;
+  a->ctx = b->ctx = ctx;
+  a->n = n_a;
+  b->n = n_b;
+  a->index_offset = offset_a;
+  b->index_offset = offset_b;
+  auto fail = [&](int rc) {
+    cb_cloud_destroy(a);
+    cb_cloud_destroy(b);
+    return rc;
+  };
+  auto upload = [&](cb_cloud* c, const float* xyz, const float* nrm, cudaStream_t s) -> int {
+    if (c->n == 0) return CB_OK;
+    CB_CUDA(cudaMemcpyAsync(c->d_raw, xyz, 3 * c->n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (nrm) CB_CUDA(cudaMemcpyAsync(c->d_raw_nrm, nrm, 3 * c->n * sizeof(float), cudaMemcpyHostToDevice, s));
+    return CB_OK;
+  };
+  // allocations are stream-ordered on the main stream; the copy stream starts after them
+  if (n_a) {
+    if (cudaMallocAsync(&a->d_raw, 3 * n_a * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+    if (normals_a && cudaMallocAsync(&a->d_raw_nrm, 3 * n_a * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+  }
+  if (n_b) {
+    if (cudaMallocAsync(&b->d_raw, 3 * n_b * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+    if (normals_b && cudaMallocAsync(&b->d_raw_nrm, 3 * n_b * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+  }
+  if (cudaEventRecord(ev.e0, ctx->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->copy_stream, ev.e0, 0) != cudaSuccess)
+    return fail(CB_ERR_CUDA);
+  int rc = upload(a, xyz_a, normals_a, ctx->stream);
+  if (rc == CB_OK) rc = upload(b, xyz_b, normals_b, ctx->copy_stream);
+  if (rc == CB_OK && cudaEventRecord(ev.e1, ctx->copy_stream) != cudaSuccess) rc = CB_ERR_CUDA;
+  if (rc == CB_OK) rc = ensure_index(a);  // host-blocking in places; the second upload proceeds meanwhile
+  if (rc == CB_OK && cudaStreamWaitEvent(ctx->stream, ev.e1, 0) != cudaSuccess) rc = CB_ERR_CUDA;
+  if (rc == CB_OK) rc = ensure_index(b);
+  if (rc == CB_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = CB_ERR_CUDA;
+  if (rc != CB_OK) {  // the failing call has set the message
+    cudaStreamSynchronize(ctx->copy_stream);
+    return fail(rc);
+  }
+  *out_a = a;
+  *out_b = b;
   return CB_OK;
 }
 

@@ -109,6 +109,7 @@ struct cb_context {
   void* d_flush = nullptr;
   size_t flush_bytes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  cudaStream_t copy_stream = nullptr;  // second stream: uploads overlapped with index builds (cb_cloud_create_pair)
   // NCCL (loaded lazily with dlopen; see nccl_dyn.cpp)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;

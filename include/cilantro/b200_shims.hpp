@@ -411,18 +411,18 @@ public:
   using Transform = RigidTransform3f;
 
   // point-to-point: (dst, src); combined: (dst, dst_normals, src[, src_normals])
-  SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src)
-      : dst_(dst), src_(src) {
+  SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src) {
+    upload(dst, nullptr, src, nullptr);
     init();
   }
   SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
-                       const ConstVectorSetMatrixMap3f& src)
-      : dst_(dst, &dst_n), src_(src) {
+                       const ConstVectorSetMatrixMap3f& src) {
+    upload(dst, &dst_n, src, nullptr);
     init();
   }
   SimpleRigidICP3fB200(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
-                       const ConstVectorSetMatrixMap3f& src, const ConstVectorSetMatrixMap3f& src_n)
-      : dst_(dst, &dst_n), src_(src, &src_n) {
+                       const ConstVectorSetMatrixMap3f& src, const ConstVectorSetMatrixMap3f& src_n) {
+    upload(dst, &dst_n, src, &src_n);
     init();
   }
   ~SimpleRigidICP3fB200() {
@@ -515,6 +515,15 @@ public:
   double getLastEstimateDeviceMilliseconds() const { return res_.gpu_ms_total; }
 
 private:
+  // both clouds in one call: the source upload overlaps the destination's grid build (cb_cloud_create_pair)
+  void upload(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f* dst_n,
+              const ConstVectorSetMatrixMap3f& src, const ConstVectorSetMatrixMap3f* src_n) {
+    const float* dn = (dst_n && dst_n->cols() == dst.cols() && dst.cols() > 0) ? dst_n->data() : nullptr;
+    const float* sn = (src_n && src_n->cols() == src.cols() && src.cols() > 0) ? src_n->data() : nullptr;
+    b200::check(cb_cloud_create_pair(b200::Context::get(), dst.data(), dn, dst.cols(), 0, src.data(), sn, src.cols(), 0,
+                                     &dst_.h, &src_.h),
+                "cb_cloud_create_pair");
+  }
   void init() {
     cb_icp_default_params(&prm_);
     prm_.metric = kMetric;

@@ -91,6 +91,13 @@ int cb_comm_ipc_detach(cb_context* ctx);
  * (a rank's shard offset; 0 on a single GPU). */
 int cb_cloud_create(cb_context* ctx, const float* xyz, const float* normals, size_t n, uint64_t index_offset,
                     cb_cloud** out);
+/* Two clouds in one call — what the constructors of the ICP classes receive (icp_common_instances.hpp:34-44:
+ * dst points [+ normals], src points [+ normals]). Same result as two cb_cloud_create calls followed by the lazy
+ * index builds, but the upload of the second cloud runs on a second stream while the grid of the first is being
+ * built (effective with pinned host buffers). Both clouds are indexed on return. */
+int cb_cloud_create_pair(cb_context* ctx, const float* xyz_a, const float* normals_a, size_t n_a, uint64_t offset_a,
+                         const float* xyz_b, const float* normals_b, size_t n_b, uint64_t offset_b, cb_cloud** out_a,
+                         cb_cloud** out_b);
 /* Same, from packed xyz already in device memory (used when inputs are HBM-resident). */
 int cb_cloud_create_from_device(cb_context* ctx, const float* d_xyz, const float* d_normals, size_t n,
                                 uint64_t index_offset, cb_cloud** out);
