@@ -79,6 +79,30 @@ def surface_cloud(n, seed=1, noise=0.0005):
     return np.stack([x, y, z], axis=1).astype(np.float32), g.astype(np.float32)
 
 
+def rigid_icp_example_pair(points, normals, seed=1):
+    """The input recipe of the reference's examples/rigid_icp.cpp:25-65 on a loaded scan (BASELINE config 1):
+    src = dst + 0.01 * U(-1,1)^3 (normals + 0.02 * U, re-normalised), dst keeps only x > -0.4, then
+    src <- tf_ref * src with tf_ref = Rz(-0.1) Ry(0.1) Rx(-0.1), t = (-0.20, -0.05, 0.10).
+    Returns dst_p, dst_n, src_p, src_n, tf_ref (3x4 float64); ICP should recover tf_ref^-1."""
+    rng = np.random.default_rng(seed)
+    p = np.asarray(points, np.float32)
+    n = np.asarray(normals, np.float32)
+    src_p = (p + np.float32(0.01) * (rng.random(p.shape, dtype=np.float32) * 2 - 1)).astype(np.float32)
+    src_n = n + np.float32(0.02) * (rng.random(n.shape, dtype=np.float32) * 2 - 1)
+    src_n = (src_n / np.linalg.norm(src_n, axis=1, keepdims=True)).astype(np.float32)
+    keep = p[:, 0] > np.float32(-0.4)
+    dst_p, dst_n = np.ascontiguousarray(p[keep]), np.ascontiguousarray(n[keep])
+
+    def rot(axis, a):
+        return np.asarray(rigid_from_axis_angle(axis, a, [0, 0, 0]))[:, :3]
+
+    R = rot([0, 0, 1], -0.1) @ rot([0, 1, 0], 0.1) @ rot([1, 0, 0], -0.1)
+    tf_ref = np.hstack([R, np.array([[-0.20], [-0.05], [0.10]])])
+    src_p = apply(tf_ref, src_p).astype(np.float32)
+    src_n = (src_n.astype(np.float64) @ R.T).astype(np.float32)
+    return dst_p, dst_n, src_p, src_n, tf_ref
+
+
 def kmeans_data(n, k, seed=1):
     """uniform [0,1)^3 points; initial centroids = first k points of a seeded shuffle (config 4)."""
     rng = np.random.default_rng(seed)
