@@ -137,3 +137,27 @@ def test_solve_rotation_and_compose(cb, orc):
 
 def test_kmeans_seed_indices_host(cb, orc):
     assert np.array_equal(cb.kmeans_seed_indices(5000, 100, 42), orc.kmeans_seed_indices(5000, 100, 42))
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under cilantro_b200/ or include/ may include, import, link or
+    dlopen it, and the shared library must not depend on it."""
+    import re
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r'#\s*include\s*[<"][^>"\n]*oracle|^\s*import\s+oracle\b|^\s*from\s+oracle\b.*\bimport\b|'
+                     r'libcilantro_oracle|libcilantro_ref_knn|\borc_[a-z_]+\s*\(', re.M)
+    offenders = []
+    for base in ("cilantro_b200", "include"):
+        for dirpath, _, files in os.walk(os.path.join(root, base)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                    continue
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                if pat.search(text):
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    lib = os.path.join(root, "cilantro_b200", "libcilantro_b200.so")
+    needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
+    assert "oracle" not in needed and "ref_knn" not in needed
