@@ -54,6 +54,7 @@ class IcpParams(C.Structure):
         ("one_to_one", C.c_int32),
         ("reserved_", C.c_int32),
         ("inlier_fraction", C.c_double),
+        ("f2s_fn", C.c_void_p),
     ]
 
 
@@ -302,13 +303,14 @@ def estimate_combined(dst_p, dst_n, src_p, idx_first, idx_second, w_pt, w_pl, ma
 
 def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, tol=1e-5, max_d2=1e-4,
         w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5, T_init=None, accum_double=False, parallel=False,
-        log=False, search_dir="second_to_first", inlier_fraction=1.0, require_reciprocal=False, one_to_one=False):
+        log=False, search_dir="second_to_first", inlier_fraction=1.0, require_reciprocal=False, one_to_one=False,
+        f2s_reference=False):
     """icp_base.hpp:68-87 driving the p2p or combined/symmetric estimator. Returns a dict."""
     dst_p, src_p = _f32(dst_p), _f32(src_p)
     dst_n = _f32(dst_n) if dst_n is not None else None
     src_n = _f32(src_n) if src_n is not None else None
     prm = IcpParams()
-    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one)
+    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one, f2s_reference)
     prm.metric = 0 if metric == "p2p" else 1
     prm.max_iter = int(max_iter)
     prm.tol = tol
@@ -341,20 +343,23 @@ def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, to
     return out
 
 
-def _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one):
+def _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one, f2s_reference=False):
     prm.search_dir = SEARCH_DIR[search_dir] if isinstance(search_dir, str) else int(search_dir)
     prm.inlier_fraction = float(inlier_fraction)
     prm.require_reciprocal = int(require_reciprocal)
     prm.one_to_one = int(one_to_one)
+    # FIRST_TO_SECOND searches: brute force (lowest index on exact ties, the CUDA path's rule) or, on request, the
+    # reference's own nanoflann with the tree over the transformed source rebuilt per call (ties: traversal order)
+    prm.f2s_fn = C.cast(ref().ref_knn1_build_query, C.c_void_p) if (f2s_reference and have_ref()) else None
 
 
 def engine_correspondences(dst_p, src_p, T, knn, max_d2, search_dir="second_to_first", inlier_fraction=1.0,
-                           require_reciprocal=False, one_to_one=False):
+                           require_reciprocal=False, one_to_one=False, f2s_reference=False):
     """CorrespondenceSearchKDTree::findCorrespondences(T).getCorrespondences(): (first, second, value)."""
     dst_p, src_p = _f32(dst_p), _f32(src_p)
     prm = IcpParams()
     prm.max_d2 = max_d2
-    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one)
+    _engine_fields(prm, search_dir, inlier_fraction, require_reciprocal, one_to_one, f2s_reference)
     cap = dst_p.shape[0] + src_p.shape[0]
     i1 = np.empty(cap, np.uint64)
     i2 = np.empty(cap, np.uint64)

@@ -514,6 +514,9 @@ struct orc_icp_params {
   int32_t one_to_one;
   int32_t reserved_;
   double inlier_fraction;
+  // FIRST_TO_SECOND / BOTH: 1-NN of the dst points among the transformed src points, tree rebuilt per call.
+  // nullptr = orc_knn1_brute; tests pass oracle/_ref's ref_knn1_build_query (the reference's own nanoflann).
+  void (*f2s_fn)(const float* ref_pts, size_t nref, const float* qry, size_t nq, float max_d2, int64_t* idx, float* d2);
 };
 
 // CorrespondenceSearchKDTree::findCorrespondences(tform) — correspondence_search_kd_tree.hpp:107-229:
@@ -537,7 +540,7 @@ static void engine_correspondences(const float* dst_p, size_t n_dst, const float
   if (dir != 0 && n_src > 0 && n_dst > 0) {
     std::vector<int64_t> j(n_dst);
     std::vector<float> v(n_dst);
-    orc_knn1_brute(src_trans, n_src, dst_p, n_dst, prm->max_d2, j.data(), v.data());
+    (prm->f2s_fn ? prm->f2s_fn : orc_knn1_brute)(src_trans, n_src, dst_p, n_dst, prm->max_d2, j.data(), v.data());
     for (size_t i = 0; i < n_dst; i++)
       if (j[i] >= 0 && v[i] < prm->max_d2) f2s.push_back({i, (size_t)j[i], v[i]});
   }

@@ -194,4 +194,14 @@ REF_API void ref_radius_batch(void* h, const float* qry, size_t nq, float r2, si
   }
 }
 
+// FIRST_TO_SECOND search of the correspondence engine (correspondence_search_kd_tree.hpp:195-204): the reference
+// builds a fresh kd-tree over the TRANSFORMED source points on every call and queries it with the destination
+// points. Same signature as orc_knn1_brute (cilantro_oracle.cpp) so that the oracle can use either.
+REF_API void ref_knn1_build_query(const float* ref_pts, size_t nref, const float* qry, size_t nq, float max_d2,
+                                  int64_t* idx, float* d2) {
+  void* t = ref_tree_build(ref_pts, nref, 10);
+  ref_knn1_radius_cb(t, qry, nq, max_d2, idx, d2);
+  ref_tree_free(t);
+}
+
 REF_API unsigned ref_nanoflann_version() { return NANOFLANN_VERSION; }

@@ -51,6 +51,34 @@ def test_fraction_and_one_to_one(orc):
     assert _pairs(orc, search_dir="both", inlier_fraction=0.75)[0] == [(0, 0), (1, 2), (0, 1)]
 
 
+def test_first_to_second_search_pinned_on_reference_nanoflann(orc):
+    """FIRST_TO_SECOND / BOTH rebuild a kd-tree over the transformed source on every call
+    (correspondence_search_kd_tree.hpp:195-204, :214-226). With oracle/_ref that search is the reference's own nanoflann
+    (tree built and queried per call); the brute-force restatement the GPU tests compare against must give the same
+    lists on data without exact ties, and the same ICP transforms."""
+    import pytest
+
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    from cilantro_b200 import synth
+
+    dst, src, _, T_ref = synth.icp_pair(20000, seed=4, noise=0.003, n_src=15000)
+    T0 = (0.7 * np.asarray(T_ref) + 0.3 * np.hstack([np.eye(3), np.zeros((3, 1))])).astype(np.float32)
+    max_d2 = np.float32((2.0 * 20000 ** (-1.0 / 3.0)) ** 2)
+    knn = orc.RefKnn(dst)
+    for mode in (dict(search_dir="first_to_second"), dict(search_dir="first_to_second", one_to_one=True),
+                 dict(search_dir="both"), dict(search_dir="both", require_reciprocal=True, inlier_fraction=0.7)):
+        a = orc.engine_correspondences(dst, src, T0, knn, max_d2, f2s_reference=True, **mode)
+        b = orc.engine_correspondences(dst, src, T0, orc.BruteKnn(dst), max_d2, f2s_reference=False, **mode)
+        assert len(a[0]) > 1000
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(a[2].view(np.uint32), b[2].view(np.uint32))
+    kw = dict(metric="p2p", max_iter=6, tol=0.0, max_d2=max_d2, search_dir="both", require_reciprocal=True)
+    ra = orc.icp(dst, src, knn, f2s_reference=True, **kw)
+    rb = orc.icp(dst, src, orc.BruteKnn(dst), f2s_reference=False, **kw)
+    assert ra["num_corr"] == rb["num_corr"] and np.array_equal(ra["T"], rb["T"])
+
+
 def test_engine_icp_recovers_a_shift(orc):
     rng = np.random.default_rng(0)
     dst = rng.random((1500, 3), dtype=np.float32)
