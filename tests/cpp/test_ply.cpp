@@ -15,6 +15,19 @@
 
 int main(int argc, char** argv) {
   const std::string dir = argc > 1 ? argv[1] : ".";
+  if (argc > 2) {
+    // a real scan (the reference's examples/test_clouds/*.ply): print what was read for the Python side to check
+    cilantro::PointCloud3f scan(argv[2]);
+    std::printf("scan %zu %d %d\n", scan.size(), (int)scan.hasNormals(), (int)scan.hasColors());
+    const size_t probe[3] = {0, scan.size() / 2, scan.size() - 1};
+    for (size_t i : probe) {
+      std::printf("v %zu %.9g %.9g %.9g", i, scan.points(0, i), scan.points(1, i), scan.points(2, i));
+      if (scan.hasNormals()) std::printf(" n %.9g %.9g %.9g", scan.normals(0, i), scan.normals(1, i), scan.normals(2, i));
+      if (scan.hasColors()) std::printf(" c %.9g %.9g %.9g", scan.colors(0, i), scan.colors(1, i), scan.colors(2, i));
+      std::printf("\n");
+    }
+    return 0;
+  }
   cilantro::PointCloud3f pc;
   const size_t N = 1000;
   pc.points.resize(3, N);
