@@ -161,3 +161,21 @@ def test_product_never_touches_the_oracle():
     lib = os.path.join(root, "cilantro_b200", "libcilantro_b200.so")
     needed = subprocess.run(["readelf", "-d", lib], capture_output=True, text=True).stdout
     assert "oracle" not in needed and "ref_knn" not in needed
+
+
+def test_library_carries_only_sm_100a_code():
+    """Built for B200 and nothing else: every embedded cubin is sm_100a (no multi-arch fat binary, no PTX-only JIT
+    path), and the hot kernels are in it."""
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    lib = os.path.join(ROOT, "cilantro_b200", "libcilantro_b200.so")
+    elfs = [ln for ln in subprocess.run(["cuobjdump", "-lelf", lib], capture_output=True, text=True).stdout.splitlines()
+            if ln.startswith("ELF file")]
+    assert elfs and all(".sm_100a.cubin" in ln for ln in elfs), elfs
+    syms = subprocess.run(["cuobjdump", "-symbols", lib], capture_output=True, text=True).stdout
+    for kernel in ("icp_pass_kernel", "kmeans_assign_kernel", "ransac_score_kernel", "moments_kernel",
+                   "normals_knn_kernel", "radix_scatter_kernel", "bin_reduce_kernel", "pairs_pass_kernel"):
+        assert kernel in syms, kernel
