@@ -104,3 +104,59 @@ def test_two_rank_sharded_icp_equals_single_process(tmp_path, orc, cb):
     # and the oracle's own ICP agrees
     ref = orc.icp(dst, src, knn, metric="p2p", max_iter=3, tol=0.0, max_d2=np.float32(0.05**2))
     assert np.linalg.norm(T0.astype(np.float64) - ref["T"]) < 1e-5
+
+
+class _FakeCtx:
+    """Stands in for capi.Context in attach_comm (no GPU here): records the calls, fails the peer mapping on demand."""
+
+    def __init__(self, capi, fail_attach):
+        self.capi, self.fail_attach, self.calls = capi, fail_attach, []
+
+    def init_comm(self, uid, rank, world):
+        assert len(uid) == 128
+        self.calls.append(("init_comm", rank, world))
+
+    def ipc_handle(self):
+        return bytes(64)
+
+    def ipc_attach(self, handles):
+        self.calls.append(("ipc_attach", len(handles)))
+        if self.fail_attach:
+            raise self.capi.CbError("no peer access")
+
+    def ipc_detach(self):
+        self.calls.append(("ipc_detach",))
+
+
+def _attach_worker(rank, world, port, out_dir, failing_rank):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    os.environ.pop("CB_NO_FUSED_EXCHANGE", None)
+    os.environ.pop("CB_TEST_IPC_FAIL_RANK", None)
+    import torch.distributed as dist
+
+    from cilantro_b200 import capi, dist as cdist
+
+    cdist.init_process_group(backend="gloo")
+    capi.comm_unique_id = lambda: bytes(128)  # the real one asks NCCL; the agreement logic is what is under test
+    ctx = _FakeCtx(capi, fail_attach=(rank == failing_rank))
+    r, w = cdist.attach_comm(ctx)
+    assert (r, w) == (rank, world)
+    with open(os.path.join(out_dir, f"calls_{failing_rank}_{rank}.txt"), "w") as f:
+        f.write(repr(ctx.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("failing_rank", [-1, 1])
+def test_attach_comm_ranks_agree_on_the_exchange_path(tmp_path, failing_rank):
+    """If the peer mapping of the fused exchange fails on ANY rank, EVERY rank must go back to the NCCL path
+    (cb_comm_ipc_detach) — a rank left on the fused path would wait for rows that never come."""
+    world = 2
+    mp.spawn(_attach_worker, args=(world, _free_port(), str(tmp_path), failing_rank), nprocs=world, join=True)
+    for rank in range(world):
+        calls = eval(open(tmp_path / f"calls_{failing_rank}_{rank}.txt").read())
+        names = [c[0] for c in calls]
+        assert names[:2] == ["init_comm", "ipc_attach"] and calls[1][1] == 64 * world
+        assert ("ipc_detach" in names) == (failing_rank >= 0), (rank, names)
