@@ -13,8 +13,11 @@ __device__ __forceinline__ constexpr int ut(int r, int c) { return r * 6 - (r * 
 
 // dp = matched destination point, (qx,qy,qz) = T * source point. load_dst_normal() / load_src_normal()
 // are only invoked when the metric needs them (has_pl / have_src_normal).
-template <int MODE, class LoadDstNormal, class LoadSrcNormal>
-__device__ __forceinline__ void accumulate_pair(double* acc, const IcpArgs& a, bool has_pt, bool has_pl,
+// Args: anything with the fields T, Tin (Rigid), dm, sm (float[3]), w_pt, w_pl — IcpArgs, or the loop kernel's
+// per-block context. kIdentityTin = true skips the (identity) inner Gauss-Newton transform of the first pass:
+// (1*x + (0*y + 0*z)) + 0 == x bit for bit for finite x.
+template <int MODE, bool kIdentityTin = false, class Args, class LoadDstNormal, class LoadSrcNormal>
+__device__ __forceinline__ void accumulate_pair(double* acc, const Args& a, bool has_pt, bool has_pl,
                                                 const float4 dp, float qx, float qy, float qz, bool have_src_normal,
                                                 LoadDstNormal load_dst_normal, LoadSrcNormal load_src_normal) {
   if constexpr (MODE == kModeP2P) {
@@ -25,11 +28,28 @@ __device__ __forceinline__ void accumulate_pair(double* acc, const IcpArgs& a, b
     acc[7] += dx * x;  acc[8] += dx * y;  acc[9] += dx * z;
     acc[10] += dy * x; acc[11] += dy * y; acc[12] += dy * z;
     acc[13] += dz * x; acc[14] += dz * y; acc[15] += dz * z;
+  } else if constexpr (MODE == kModeP2PCentered) {
+    // the same 16 moments about the pivots dm (dst mean) and sm (T * src mean): no cancellation in
+    // sigma = (sum d' q'^T)/n - mu_d' mu_q'^T for clouds far from the origin (solve_core.hpp)
+    const double dx = (double)dp.x - (double)a.dm[0], dy = (double)dp.y - (double)a.dm[1], dz = (double)dp.z - (double)a.dm[2];
+    const double x = (double)qx - (double)a.sm[0], y = (double)qy - (double)a.sm[1], z = (double)qz - (double)a.sm[2];
+    acc[0] += 1.0;
+    acc[1] += dx; acc[2] += dy; acc[3] += dz;
+    acc[4] += x;  acc[5] += y;  acc[6] += z;
+    acc[7] += dx * x;  acc[8] += dx * y;  acc[9] += dx * z;
+    acc[10] += dy * x; acc[11] += dy * y; acc[12] += dy * z;
+    acc[13] += dz * x; acc[14] += dz * y; acc[15] += dz * z;
   } else if constexpr (MODE == kModeCombined) {
     // d = dst - dst_mean ; s = Tin * (q - T*src_mean)           transform_estimation.hpp:300,304
     const float d0 = __fsub_rn(dp.x, a.dm[0]), d1 = __fsub_rn(dp.y, a.dm[1]), d2 = __fsub_rn(dp.z, a.dm[2]);
     float s0, s1, s2;
-    apply_rigid(a.Tin, __fsub_rn(qx, a.sm[0]), __fsub_rn(qy, a.sm[1]), __fsub_rn(qz, a.sm[2]), s0, s1, s2);
+    if constexpr (kIdentityTin) {
+      s0 = __fsub_rn(qx, a.sm[0]);
+      s1 = __fsub_rn(qy, a.sm[1]);
+      s2 = __fsub_rn(qz, a.sm[2]);
+    } else {
+      apply_rigid(a.Tin, __fsub_rn(qx, a.sm[0]), __fsub_rn(qy, a.sm[1]), __fsub_rn(qz, a.sm[2]), s0, s1, s2);
+    }
     const float v0 = __fadd_rn(d0, s0), v1 = __fadd_rn(d1, s1), v2 = __fadd_rn(d2, s2);
     const float e0 = __fsub_rn(d0, s0), e1 = __fsub_rn(d1, s1), e2 = __fsub_rn(d2, s2);
     acc[0] += 1.0;
@@ -69,7 +89,13 @@ __device__ __forceinline__ void accumulate_pair(double* acc, const IcpArgs& a, b
         const float4 sn = load_src_normal();
         float r0, r1, r2, t0, t1, t2;
         rotate_rigid(a.T, sn.x, sn.y, sn.z, r0, r1, r2);
-        rotate_rigid(a.Tin, r0, r1, r2, t0, t1, t2);
+        if constexpr (kIdentityTin) {
+          t0 = r0;
+          t1 = r1;
+          t2 = r2;
+        } else {
+          rotate_rigid(a.Tin, r0, r1, r2, t0, t1, t2);
+        }
         n0 = __fadd_rn(n0, t0);
         n1 = __fadd_rn(n1, t1);
         n2 = __fadd_rn(n2, t2);

@@ -1,0 +1,339 @@
+// Product O(1) linear algebra (double precision), compiled for the HOST and for the DEVICE: the solves the
+// reference performs with Eigen once per ICP iteration. The device-resident ICP loop (icp_loop.cu) runs them
+// in the last warp of the iteration's kernel, so that the iterations can be enqueued back to back without a
+// host round trip; the host loop (engine modes, inner Gauss-Newton iterations, cb_solve_*) calls the same code.
+//   3x3 SVD              one-sided (Hestenes) Jacobi       <- Eigen::JacobiSVD
+//                                                             (registration/transform_estimation.hpp:36-44,
+//                                                              core/space_transformations.hpp:43-51)
+//   6x6 symmetric solve  Gaussian elimination, partial pivoting <- AtA.ldlt().solve(Atb) (:346)
+//   3x3 symmetric eigen  via the SVD of the PSD covariance  <- Eigen::SelfAdjointEigenSolver
+//                                                             (core/principal_component_analysis.hpp:77)
+#pragma once
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#else
+#define CB_HD inline
+#endif
+
+namespace cb {
+namespace la {
+
+struct Mat3 {
+  double m[3][3];
+  CB_HD static Mat3 identity() {
+    Mat3 r{};
+    r.m[0][0] = r.m[1][1] = r.m[2][2] = 1.0;
+    return r;
+  }
+};
+
+CB_HD Mat3 mul(const Mat3& a, const Mat3& b) {
+  Mat3 r{};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[i][j] = a.m[i][0] * b.m[0][j] + a.m[i][1] * b.m[1][j] + a.m[i][2] * b.m[2][j];
+  return r;
+}
+
+CB_HD Mat3 transpose(const Mat3& a) {
+  Mat3 r{};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r.m[i][j] = a.m[j][i];
+  return r;
+}
+
+CB_HD double det(const Mat3& a) {
+  return a.m[0][0] * (a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1]) -
+         a.m[0][1] * (a.m[1][0] * a.m[2][2] - a.m[1][2] * a.m[2][0]) +
+         a.m[0][2] * (a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0]);
+}
+
+// A = U diag(sv) V^T, sv descending. U's columns belonging to (numerically) zero singular values
+// are completed to a right- or left-handed frame as needed by the callers below, which only use
+// u0, u1 and u0 x u1.
+struct Svd {
+  Mat3 U, V;
+  double sv[3];
+};
+
+CB_HD Svd svd_hestenes(const Mat3& A) {
+  double G[3][3], V[3][3];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      G[i][j] = A.m[i][j];
+      V[i][j] = (i == j) ? 1.0 : 0.0;
+    }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int i = 0; i < 3; i++) {
+          alpha += G[i][p] * G[i][p];
+          beta += G[i][q] * G[i][q];
+          gamma += G[i][p] * G[i][q];
+        }
+        if (gamma == 0.0 || fabs(gamma) <= 1e-17 * sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        for (int i = 0; i < 3; i++) {
+          const double gp = G[i][p], gq = G[i][q];
+          G[i][p] = c * gp - s * gq;
+          G[i][q] = s * gp + c * gq;
+          const double vp = V[i][p], vq = V[i][q];
+          V[i][p] = c * vp - s * vq;
+          V[i][q] = s * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  double nrm[3];
+  int order[3] = {0, 1, 2};
+  for (int j = 0; j < 3; j++) nrm[j] = sqrt(G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j]);
+  // stable descending order of three values (insertion)
+  for (int a = 1; a < 3; a++)
+    for (int b = a; b > 0 && nrm[order[b]] > nrm[order[b - 1]]; b--) {
+      const int t = order[b];
+      order[b] = order[b - 1];
+      order[b - 1] = t;
+    }
+  Svd r;
+  for (int j = 0; j < 3; j++) {
+    const int s = order[j];
+    r.sv[j] = nrm[s];
+    for (int i = 0; i < 3; i++) {
+      r.V.m[i][j] = V[i][s];
+      r.U.m[i][j] = (nrm[s] > 0.0) ? G[i][s] / nrm[s] : 0.0;
+    }
+  }
+  // complete U where singular values vanish (rank-deficient input)
+  const double tiny = 1e-14 * (r.sv[0] > 1e-300 ? r.sv[0] : 1e-300);
+  if (r.sv[0] <= 0.0) {
+    r.U = Mat3::identity();
+  } else {
+    if (r.sv[1] <= tiny) {  // pick any unit vector orthogonal to u0
+      int k = 0;
+      for (int i = 1; i < 3; i++)
+        if (fabs(r.U.m[i][0]) < fabs(r.U.m[k][0])) k = i;
+      double e[3] = {0, 0, 0};
+      e[k] = 1.0;
+      double d = r.U.m[k][0];
+      double v[3] = {e[0] - d * r.U.m[0][0], e[1] - d * r.U.m[1][0], e[2] - d * r.U.m[2][0]};
+      double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+      for (int i = 0; i < 3; i++) r.U.m[i][1] = v[i] / n;
+    }
+    if (r.sv[2] <= tiny) {  // u2 = u0 x u1 (sign irrelevant to the callers)
+      r.U.m[0][2] = r.U.m[1][0] * r.U.m[2][1] - r.U.m[2][0] * r.U.m[1][1];
+      r.U.m[1][2] = r.U.m[2][0] * r.U.m[0][1] - r.U.m[0][0] * r.U.m[2][1];
+      r.U.m[2][2] = r.U.m[0][0] * r.U.m[1][1] - r.U.m[1][0] * r.U.m[0][1];
+    }
+  }
+  return r;
+}
+
+// U V^T with the reflection repaired by negating column `flip_col` of U when det(U V) < 0:
+// flip_col = 2 is the Kabsch rule (transform_estimation.hpp:38-41), flip_col = 0 is
+// LinearTransform::rotation() (space_transformations.hpp:45-48).
+CB_HD Mat3 rotation_from_svd(const Svd& s, int flip_col) {
+  Mat3 U = s.U;
+  if (det(U) * det(s.V) < 0.0)
+    for (int i = 0; i < 3; i++) U.m[i][flip_col] = -U.m[i][flip_col];
+  return mul(U, transpose(s.V));
+}
+
+// Solve the 6x6 system A x = b (A symmetric, given full row-major). Returns false when singular
+// to working precision (x is then the least-damaged elimination result, like a failed LDLT).
+CB_HD bool solve6(const double* A_in, const double* b_in, double* x) {
+  const int n = 6;
+  double M[6][7];
+  for (int i = 0; i < n; i++) {
+    for (int j = 0; j < n; j++) M[i][j] = A_in[i * n + j];
+    M[i][n] = b_in[i];
+  }
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    for (int i = k + 1; i < n; i++)
+      if (fabs(M[i][k]) > fabs(M[piv][k])) piv = i;
+    if (piv != k)
+      for (int j = 0; j <= n; j++) {
+        const double t = M[k][j];
+        M[k][j] = M[piv][j];
+        M[piv][j] = t;
+      }
+    const double d = M[k][k];
+    if (d == 0.0 || !(d == d)) {
+      ok = false;
+      continue;
+    }
+    for (int i = k + 1; i < n; i++) {
+      const double f = M[i][k] / d;
+      if (f == 0.0) continue;
+      for (int j = k; j <= n; j++) M[i][j] -= f * M[k][j];
+    }
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double s = M[i][n];
+    for (int j = i + 1; j < n; j++) s -= M[i][j] * x[j];
+    x[i] = (M[i][i] != 0.0) ? s / M[i][i] : 0.0;
+  }
+  return ok;
+}
+
+}  // namespace la
+
+// ---- the per-iteration solves (shared by host_solve.cpp and the device loop) -------------------------------
+namespace sc {
+
+CB_HD void t34_identity(float* T) {
+  for (int i = 0; i < 12; i++) T[i] = 0.f;
+  T[0] = T[5] = T[10] = 1.f;
+}
+
+// estimateTransformPointToPointMetric from reduced moments (transform_estimation.hpp:25-47). The moments are
+// taken about the pivots (pd, pq) — s = {n, sum (d - pd), sum (q - pq), sum (d - pd)(q - pq)^T} — so that
+// clouds far from the origin do not cancel in sigma = (sum d' q'^T)/n - mu_d' mu_q'^T (pivots of zero give the
+// raw-moment form):  R = U V^T (reflection: last column of U), t = (pd + mu_d') - R (pq + mu_q').
+CB_HD bool kabsch_from_moments(const double* s, const float* pd, const float* pq, float* T) {
+  const double n = s[0];
+  if (!(n > 0.0)) {  // :20-23
+    t34_identity(T);
+    return false;
+  }
+  double mud[3], muq[3];
+  for (int r = 0; r < 3; r++) {
+    mud[r] = s[1 + r] / n;
+    muq[r] = s[4 + r] / n;
+  }
+  la::Mat3 sigma;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) sigma.m[r][c] = s[7 + r * 3 + c] / n - mud[r] * muq[c];
+  const la::Svd svd = la::svd_hestenes(sigma);
+  const la::Mat3 R = la::rotation_from_svd(svd, 2);
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) T[r * 4 + c] = (float)R.m[r][c];
+  for (int r = 0; r < 3; r++) {
+    double t = mud[r] + (pd ? (double)pd[r] : 0.0);
+    for (int c = 0; c < 3; c++) t -= (double)T[r * 4 + c] * (muq[c] + (pq ? (double)pq[c] : 0.0));
+    T[r * 4 + 3] = (float)t;
+  }
+  return n >= 3.0;  // :47
+}
+
+// One Gauss-Newton update (transform_estimation.hpp:346-357):
+//   d_theta = AtA^-1 Atb ; theta = atan(|w|) ; Ra = AngleAxis(theta, w/|w|) ; ta = cos(theta) v
+//   T_out = Ra * Translation(ta) * Ra * T_in
+CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout, float* dtheta_norm) {
+  double A[36], b[6], x[6];
+  int k = 1;
+  for (int r = 0; r < 6; r++)
+    for (int c = r; c < 6; c++) {
+      A[r * 6 + c] = s28[k];
+      A[c * 6 + r] = s28[k];
+      ++k;
+    }
+  for (int r = 0; r < 6; r++) b[r] = s28[22 + r];
+  const bool ok = la::solve6(A, b, x);
+  float dth[6];
+  for (int i = 0; i < 6; i++) dth[i] = (float)x[i];  // the reference holds d_theta in fp32
+  const double na = sqrt((double)dth[0] * dth[0] + (double)dth[1] * dth[1] + (double)dth[2] * dth[2]);
+  const double theta = atan(na);
+  double ax[3] = {0, 0, 0};
+  if (na > 0.0)
+    for (int i = 0; i < 3; i++) ax[i] = dth[i] / na;
+  const double c = cos(theta), sn = sin(theta), k1 = 1.0 - c;
+  la::Mat3 Ra;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Ra.m[i][j] = k1 * ax[i] * ax[j] + (i == j ? c : 0.0);
+  Ra.m[0][1] -= sn * ax[2];
+  Ra.m[0][2] += sn * ax[1];
+  Ra.m[1][0] += sn * ax[2];
+  Ra.m[1][2] -= sn * ax[0];
+  Ra.m[2][0] -= sn * ax[1];
+  Ra.m[2][1] += sn * ax[0];
+  la::Mat3 L;
+  double t0[3];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) L.m[i][j] = Tin[i * 4 + j];
+    t0[i] = Tin[i * 4 + 3];
+  }
+  const la::Mat3 RR = la::mul(Ra, Ra);
+  const la::Mat3 Lo = la::mul(RR, L);
+  double t1[3], t2[3];
+  for (int i = 0; i < 3; i++)
+    t1[i] = Ra.m[i][0] * t0[0] + Ra.m[i][1] * t0[1] + Ra.m[i][2] * t0[2] + c * (double)dth[3 + i];
+  for (int i = 0; i < 3; i++) t2[i] = Ra.m[i][0] * t1[0] + Ra.m[i][1] * t1[1] + Ra.m[i][2] * t1[2];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) Tout[i * 4 + j] = (float)Lo.m[i][j];
+    Tout[i * 4 + 3] = (float)t2[i];
+  }
+  double nn = 0;
+  for (int i = 0; i < 6; i++) nn += (double)dth[i] * dth[i];
+  if (dtheta_norm) *dtheta_norm = (float)sqrt(nn);
+  return ok;
+}
+
+// tform = Translation(dst_mean) * tform * Translation(-src_mean)   (transform_estimation.hpp:361/365)
+CB_HD void uncenter(float* T, const float* dst_mean, const float* src_mean) {
+  for (int i = 0; i < 3; i++) {
+    double t = T[i * 4 + 3];
+    for (int k = 0; k < 3; k++) t -= (double)T[i * 4 + k] * (double)src_mean[k];
+    T[i * 4 + 3] = (float)(t + (double)dst_mean[i]);
+  }
+}
+
+// LinearTransform::rotation() (core/space_transformations.hpp:43-51) on T's linear part
+CB_HD void reorthonormalize(float* T) {
+  la::Mat3 A;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A.m[i][j] = T[i * 4 + j];
+  const la::Mat3 R = la::rotation_from_svd(la::svd_hestenes(A), 0);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) T[i * 4 + j] = (float)R.m[i][j];
+}
+
+// out = A * B (out may alias either)
+CB_HD void compose(const float* A, const float* B, float* out) {
+  float r[12];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += (double)A[i * 4 + k] * (double)B[k * 4 + j];
+      r[i * 4 + j] = (float)s;
+    }
+    double s = A[i * 4 + 3];
+    for (int k = 0; k < 3; k++) s += (double)A[i * 4 + k] * (double)B[k * 4 + 3];
+    r[i * 4 + 3] = (float)s;
+  }
+  for (int i = 0; i < 12; i++) out[i] = r[i];
+}
+
+// sqrt(|R - I|_F^2 + |t|^2)   (icp_single_transform_combined_metric.hpp:214-216)
+CB_HD float update_norm(const float* T) {
+  float dn = 0.f;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) {
+      const float e = T[r * 4 + c] - (r == c ? 1.f : 0.f);
+      dn += e * e;
+    }
+    dn += T[r * 4 + 3] * T[r * 4 + 3];
+  }
+  return sqrtf(dn);
+}
+
+// q = R p + t in the contract order of the query transform
+CB_HD void apply_point(const float* T, const float* p, float* q) {
+#if defined(__CUDA_ARCH__)
+  for (int r = 0; r < 3; r++)
+    q[r] = __fadd_rn(__fadd_rn(__fmul_rn(T[r * 4], p[0]), __fadd_rn(__fmul_rn(T[r * 4 + 1], p[1]), __fmul_rn(T[r * 4 + 2], p[2]))),
+                     T[r * 4 + 3]);
+#else
+  for (int r = 0; r < 3; r++) q[r] = (T[r * 4] * p[0] + (T[r * 4 + 1] * p[1] + T[r * 4 + 2] * p[2])) + T[r * 4 + 3];
+#endif
+}
+
+}  // namespace sc
+}  // namespace cb
