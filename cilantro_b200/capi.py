@@ -37,7 +37,7 @@ class IcpParams(C.Structure):
         ("search_dir", C.c_int32),
         ("require_reciprocal", C.c_int32),
         ("one_to_one", C.c_int32),
-        ("reserved_", C.c_int32),
+        ("host_loop", C.c_int32),
         ("inlier_fraction", C.c_double),
     ]
 
@@ -366,7 +366,7 @@ def transform_points(ctx, T, xyz):
 
 def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5,
                T_init=None, flush_l2=False, timing=1, search_dir="second_to_first", inlier_fraction=1.0,
-               require_reciprocal=False, one_to_one=False):
+               require_reciprocal=False, one_to_one=False, host_loop=False):
     p = IcpParams()
     lib().cb_icp_default_params(C.byref(p))
     p.metric = 0 if metric == "p2p" else 1
@@ -385,6 +385,7 @@ def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=
     p.inlier_fraction = float(inlier_fraction)
     p.require_reciprocal = int(require_reciprocal)
     p.one_to_one = int(one_to_one)
+    p.host_loop = int(host_loop)
     return p
 
 

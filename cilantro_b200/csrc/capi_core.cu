@@ -3,6 +3,7 @@
 #include "icp_kernels.cuh"
 #include "stats_kernels.cuh"
 #include "host_solve.hpp"
+#include "icp_object.hpp"
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -84,9 +85,23 @@ static int setup_exchange(cb_context* ctx) {
   return CB_OK;
 }
 
-bool arm_exchange(cb_context* ctx, Exchange* ex) {
+// Bound of the in-kernel wait for the peers' rows (reduce.cuh, exchange_rows): CB_EXCHANGE_TIMEOUT_MS, default 20 s.
+unsigned long long exchange_timeout_ns() {
+  static const unsigned long long ns = [] {
+    const char* e = getenv("CB_EXCHANGE_TIMEOUT_MS");
+    const double ms = e ? atof(e) : 20000.0;
+    return ms > 0 ? (unsigned long long)(ms * 1e6) : 0ull;
+  }();
+  return ns;
+}
+
+bool exchange_available(const cb_context* ctx) {
   static const bool disabled = getenv("CB_NO_FUSED_EXCHANGE") != nullptr;  // A/B switch for measurements
-  if (!ctx->ex_ready || disabled) return false;
+  return ctx->ex_ready && !disabled;
+}
+
+bool arm_exchange(cb_context* ctx, Exchange* ex) {
+  if (!exchange_available(ctx)) return false;
   ex->enabled = 1;
   ex->rank = ctx->rank;
   ex->world = ctx->world;
@@ -98,6 +113,7 @@ bool arm_exchange(cb_context* ctx, Exchange* ex) {
   // CB_TRACE_EXCHANGE=1: %globaltimer stamps of the last 64 passes in the mapped mailbox page
   static const bool trace = getenv("CB_TRACE_EXCHANGE") != nullptr;
   ex->trace = trace ? ctx->h_sync + 64 + 4 * (ctx->seq % 64) : nullptr;
+  ex->timeout_ns = exchange_timeout_ns();
   return true;
 }
 
@@ -106,6 +122,12 @@ int wait_exchange(cb_context* ctx, int count, double* out) {
   const unsigned long long want = ctx->seq;
   unsigned long long spins = 0;
   while (*flag != want) {
+    if (*flag == (want | (1ull << 63))) {  // the kernel gave up waiting for a peer's row (reduce.cuh, exchange_rows)
+      set_error("fused exchange: a peer rank did not deliver its row of pass %llu in time (rank %d of %d)", want,
+                ctx->rank, ctx->world);
+      ctx->ex_ready = false;
+      return CB_ERR_NCCL;
+    }
     if ((++spins & 0x3ffffull) == 0) {  // every ~0.3 ms: make sure the stream has not faulted or finished without us
       cudaError_t q = cudaStreamQuery(ctx->stream);
       if (q != cudaSuccess && q != cudaErrorNotReady) {
@@ -137,26 +159,6 @@ static Rigid to_rigid(const float* T12) { return rigid_from_t12(T12); }
 }  // namespace cb
 
 using namespace cb;
-
-struct cb_icp {
-  cb_context* ctx = nullptr;
-  const cb_cloud* dst = nullptr;
-  const cb_cloud* src = nullptr;
-  float dst_mean[3] = {0, 0, 0};
-  float src_mean[3] = {0, 0, 0};
-  int* d_nn_pos = nullptr;  // per sorted src point: sorted dst position of its match, -1 none
-  float* d_nn_d2 = nullptr;
-  bool nn_valid = false;    // a search has run; T_search / max_d2_search describe it
-  bool nn_stored = false;   // d_nn_pos / d_nn_d2 hold that search's per-query result
-  bool warm_ok = false;     // d_nn_pos holds the previous iteration's matches of THIS estimate() call
-  float T_search[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-  float max_d2_search = 0.f;
-  cb::EnginePairs pairs;    // correspondence list of the last iteration in a non-default engine mode
-  bool engine_last = false; // the last estimate() went through icp_engine.cu
-  double search_ms = 0;  // CUDA-event time of the fused search+accumulate kernels of the last estimate()
-  std::vector<cudaEvent_t> events;
-  std::vector<double> iter_ms;
-};
 
 extern "C" {
 
@@ -595,6 +597,9 @@ void cb_icp_destroy(cb_icp* icp) {
   if (icp->d_nn_pos) cudaFreeAsync(icp->d_nn_pos, icp->ctx->stream);
   if (icp->d_nn_d2) cudaFreeAsync(icp->d_nn_d2, icp->ctx->stream);
   engine_release_pairs(icp->ctx, &icp->pairs);
+  if (icp->d_state) cudaFree(icp->d_state);
+  if (icp->d_miss_mask) cudaFree(icp->d_miss_mask);
+  if (icp->h_state) cudaFreeHost(icp->h_state);
   for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
   delete icp;
 }
@@ -722,6 +727,15 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   CB_CHECK(prm->metric == CB_ICP_POINT_TO_POINT || prm->metric == CB_ICP_COMBINED, CB_ERR_INVALID, "bad metric");
   cb_context* ctx = icp->ctx;
   CB_CUDA(cudaSetDevice(ctx->device));
+  {
+    // Default correspondence engine, one Gauss-Newton step per iteration (the reference's defaults): the
+    // device-resident loop (icp_loop.cu). CB_HOST_LOOP=1 keeps the host-driven loop below for A/B measurements;
+    // engine modes, inner Gauss-Newton iterations and multi-rank runs without the fused exchange always use it.
+    static const bool host_loop = getenv("CB_HOST_LOOP") != nullptr;
+    const bool one_step = prm->metric == CB_ICP_POINT_TO_POINT || prm->max_opt_iter == 1;
+    if (!host_loop && !prm->host_loop && !engine_mode(prm) && one_step && (ctx->world == 1 || exchange_available(ctx)))
+      return icp_loop_estimate(icp, prm, res);
+  }
   const uint64_t launches0 = ctx->launches;
   const int max_iter = std::max(prm->max_iter, 0);
   // Optional CUDA-event instrumentation, ONE bracket (2 events) per iteration: timing 1 = whole

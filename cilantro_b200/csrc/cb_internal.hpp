@@ -60,6 +60,7 @@ struct Exchange {
   double* host_vals;                       // mapped pinned [32]
   unsigned long long* host_flag;           // mapped pinned
   unsigned long long* trace;               // optional (CB_TRACE_EXCHANGE): 4 x %globaltimer stamps per pass
+  unsigned long long timeout_ns;           // bound of the in-kernel wait for the peers' rows (0 = unbounded)
 };
 
 // Device scratch of the two-level grid reduction (reduce.cuh), owned by the context.
@@ -163,6 +164,7 @@ int get_reduce_scratch(cb_context* ctx, int blocks, int nv, ReduceScratch* out);
 // Arms the fused exchange for the next pass (bumps ctx->seq) when the tables are ready; returns
 // whether it did. wait_exchange() then blocks the host until that pass published its totals.
 bool arm_exchange(cb_context* ctx, Exchange* ex);
+bool exchange_available(const cb_context* ctx);  // fused exchange usable (tables mapped, not switched off)
 int wait_exchange(cb_context* ctx, int count, double* out);
 
 // Scoped stream-ordered scratch: everything alloc()ed is cudaFreeAsync()ed on the context's stream when the

@@ -1,0 +1,605 @@
+// Device-resident rigid ICP loop (product code, sm_100a).
+//
+// IterativeClosestPointBase::estimate() (registration/icp_base.hpp:68-87) for the default correspondence engine:
+// ONE kernel per ICP iteration and NO host round trip between iterations. The kernel of iteration k
+//   1. reads the current estimate T_k from device memory (LoopState),
+//   2. finds every source point's correspondence under T_k (below),
+//   3. accumulates the estimator's moments and reduces them warp -> block -> grid in a fixed order,
+//   4. in the ONE warp that finishes the grid reduction: all-reduces the 16 / 28 totals with the peer ranks over
+//      NVLink peer memory (reduce.cuh, bounded wait), then solves on the device — Kabsch / one Gauss-Newton step,
+//      rotation() re-orthonormalisation, compose, update norm, convergence test (solve_core.hpp; the same code the
+//      host loop runs) — and writes T_{k+1} back to LoopState.
+// The host enqueues the launches back to back and reads LoopState once per batch; launches after convergence
+// return at once. With several ranks every rank solves the same totals redundantly -> bit-identical transforms.
+//
+// Correspondences WITHOUT a search (exact). Every search also returns an EXCLUSION bound: a radius r such that
+// every reference point other than the match is at least r away from the query (warp_search_wide.cuh). The next
+// iteration moves the query by delta = |T_{k+1} s - T_k s|, so every other point is still at least r - delta away
+// (triangle inequality); if the cached match's distance under T_{k+1} — evaluated with the contract arithmetic,
+// i.e. the very number the search would compute for it — is below that, the match is provably still the unique
+// nearest neighbour and its (index, d2) is what the full search would return, bit for bit. Only the queries
+// that fail the test are searched again; they are compacted over the block first, so the search runs on dense
+// warps. All bounds are rounded conservatively (directed rounding + 2^-18 relative margins, far above the
+// 6-ulp error of the fp32 distance evaluation); an exact tie can never pass the strict test.
+// As ICP converges the per-iteration motion shrinks geometrically and almost every query takes the cached path:
+// the iteration becomes one streaming pass (16 B query + 8 B cache + one 16 B gather per source point).
+#include "icp_accumulate.cuh"
+#include "icp_kernels.cuh"
+#include "icp_object.hpp"
+#include "reduce.cuh"
+#include "solve_core.hpp"
+#include "warp_search_wide.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace cb {
+
+namespace {
+
+constexpr int kBlock = kReduceBlock;
+#ifndef CB_LOOP_QPT
+#define CB_LOOP_QPT 4
+#endif
+constexpr int kQptWarm = CB_LOOP_QPT;  // 256-query chunks per block of the search kernel once the cache is warm
+constexpr float kUp18 = 1.0000038146972656f;    // 1 + 2^-18
+constexpr float kDown18 = 0.9999961853027344f;  // 1 - 2^-18
+constexpr float kDown17 = 0.9999923706054688f;  // 1 - 2^-17
+
+struct LoopArgs {
+  GridView dst;
+  const float4* src_pts;  // cell-sorted query cloud; .w = original index bits
+  const float4* src_nrm;  // same order, or nullptr (symmetric metric when set)
+  uint32_t n_src;
+  float max_d2, w_pt, w_pl, tol;
+  float dm[3];        // dst_mean_
+  float src_mean[3];  // src_mean_ (the kernel applies the current transform)
+  int has_pt, has_pl;  // combined metric: which terms are on
+  int bail;            // plane terms wanted but dst has no normals -> identity update (transform_estimation.hpp:269-272)
+  uint32_t* miss_mask; // one word per 32 consecutive sorted queries: bit set = the cached pass could not decide it
+  int* cache_pos;      // per sorted query: sorted dst position of its match (-1 none)
+  float* cache_r;      // per sorted query: every OTHER dst point is at least this far away (<= 0: unknown)
+  float slack_first, slack_min, slack_max;  // widening of the search beyond the nearest distance (warp_search_wide.cuh)
+  LoopState* st;
+  ReduceScratch rs;
+  int trace;  // CB_LOOP_TRACE: fill LoopState::trace
+};
+
+// per-block copy of the loop state; also the `Args` of accumulate_pair (T, dm, sm, w_pt, w_pl)
+struct BlockCtx {
+  Rigid T, Tp;
+  float dm[3], sm[3];
+  float w_pt, w_pl;
+  int have_prev, done;
+};
+
+__device__ __forceinline__ Rigid rigid_from_t12_dev(const float* T12) {
+  Rigid r;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) r.r[i * 3 + j] = __ldcg(T12 + i * 4 + j);
+    r.t[i] = __ldcg(T12 + i * 4 + 3);
+  }
+  return r;
+}
+
+// The serial epilogue of an iteration (one thread): totals -> update -> new state. Kept out of line so that its
+// double-precision temporaries do not set the register count of the search kernel.
+template <int MODE>
+__device__ __noinline__ void loop_solve(const LoopArgs* ap, const BlockCtx* cxp, const double* s, int late,
+                                        unsigned long long seq) {
+  const LoopArgs& a = *ap;
+  const BlockCtx& cx = *cxp;
+  LoopState* st = a.st;
+  if (late) {  // a peer's row never arrived (reduce.cuh, exchange_rows)
+    st->error = CB_ERR_NCCL;
+    st->done = 2;
+    __threadfence();
+    return;
+  }
+  float T[12], Titer[12], Tn[12];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) T[i * 4 + j] = cx.T.r[i * 3 + j];
+    T[i * 4 + 3] = cx.T.t[i];
+  }
+  if (MODE == kModeP2PCentered) {
+    sc::kabsch_from_moments(s, cx.dm, cx.sm, Titer);  // transform_estimation.hpp:12-48
+  } else {
+    // estimateTransformCombinedMetric, max_iter = 1 (transform_estimation.hpp:238-367 / :608-739)
+    const bool has_terms = s[0] > 0.0 && (a.has_pt || a.has_pl);
+    if (!has_terms || a.bail) {
+      sc::t34_identity(Titer);
+    } else {
+      float I[12], dn = 0.f;
+      sc::t34_identity(I);
+      sc::gauss_newton_update(s, I, Titer, &dn);
+      sc::uncenter(Titer, cx.dm, cx.sm);
+    }
+  }
+  sc::reorthonormalize(Titer);                  // icp_single_transform_combined_metric.hpp:207-211
+  sc::compose(Titer, T, Tn);                    // :213
+  const float delta = sc::update_norm(Titer);   // :214-216
+  for (int i = 0; i < 12; i++) {
+    st->T_prev[i] = T[i];
+    st->T[i] = Tn[i];
+    st->Titer[i] = Titer[i];
+  }
+  for (int i = 0; i < 28; i++) st->sums[i] = (i < (MODE == kModeP2PCentered ? kP2PValues : kCombinedValues)) ? s[i] : 0.0;
+  st->last_delta = delta;
+  st->iters = st->iters + 1;
+  st->n_corr = s[0];
+  st->have_prev = 1;
+  st->xseq = seq;
+  if (delta < a.tol) st->done = 1;  // icp_base.hpp:83
+  if (a.trace) st->trace[(st->iters - 1) & 63][3] = global_timer_ns();
+  __threadfence();
+}
+
+// One chunk of <= 256 queued queries of the tile: lane-dense wide search and cache update. Returns the searching
+// thread's pair: query index i, transformed query q, match position pos (-1 none / inactive lane).
+struct ChunkPair {
+  uint32_t i;
+  int pos;
+  float qx, qy, qz;
+};
+
+template <bool kCold>
+__device__ __forceinline__ ChunkPair search_chunk_body(const LoopArgs& a, const BlockCtx& cx, WideSearchSmem* wsm,
+                                                       const unsigned short* queue, unsigned int c, unsigned int total,
+                                                       uint32_t base) {
+  const unsigned int tid = threadIdx.x;
+  const bool act = c + tid < total;
+  const unsigned int slot = act ? (kCold ? c + tid : (unsigned int)queue[c + tid]) : 0u;
+  ChunkPair cp;
+  cp.i = base + slot;
+  cp.pos = -1;
+  cp.qx = cp.qy = cp.qz = 0.f;
+  float slack = a.slack_first;
+  int sd = -1;
+  if (act) {
+    const float4 s = __ldg(a.src_pts + cp.i);
+    apply_rigid(cx.T, s.x, s.y, s.z, cp.qx, cp.qy, cp.qz);
+    if (!kCold) {
+      float ox, oy, oz;
+      apply_rigid(cx.Tp, s.x, s.y, s.z, ox, oy, oz);
+      const float ex = __fsub_rn(cp.qx, ox), ey = __fsub_rn(cp.qy, oy), ez = __fsub_rn(cp.qz, oz);
+      const float dl = __fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex))));
+      // the next step is expected to be about half of this one, and a hit needs r - (motion) > d: widen by 2 x
+      slack = fminf(fmaxf(__fmul_rn(2.f, dl), a.slack_min), a.slack_max);
+      sd = a.cache_pos[cp.i];
+    }
+  }
+  const WideBest wb = warp_grid_nearest_wide(a.dst, *wsm, act, cp.qx, cp.qy, cp.qz, a.max_d2, sd, slack);
+  if (act) {
+    cp.pos = (wb.idx >= 0 && wb.d2 < a.max_d2) ? wb.pos : -1;
+    a.cache_pos[cp.i] = cp.pos;
+    a.cache_r[cp.i] = (wb.D2 > 0.f) ? __fmul_rd(__fsqrt_rd(wb.D2), kDown18) : 0.f;
+  }
+  return cp;
+}
+
+// Out-of-line copy for the chunks beyond the first of a tile (more than 256 of its queries need a search: rare once
+// the cache is warm). Behind a pointer the grid parameters are no longer constant-bank operands and ptxas spills
+// kilobytes per thread at this register budget, and so it did with the inline body inside a loop (loop-invariant
+// parameter loads hoisted into registers); the first chunk therefore stays inline and loop-free in the kernel.
+__device__ __noinline__ void search_chunk_far(const LoopArgs* ap, const BlockCtx* cxp, WideSearchSmem* wsm,
+                                              const unsigned short* queue, unsigned int c, unsigned int total,
+                                              uint32_t base, ChunkPair* out) {
+  *out = search_chunk_body<false>(*ap, *cxp, wsm, queue, c, total, base);
+}
+
+// thread 0 of a block: LoopState -> shared BlockCtx
+__device__ __forceinline__ void load_block_ctx(const LoopArgs& a, BlockCtx& cx) {
+  cx.done = __ldcg(&a.st->done);
+  cx.have_prev = __ldcg(&a.st->have_prev);
+  cx.T = rigid_from_t12_dev(a.st->T);
+  cx.Tp = rigid_from_t12_dev(a.st->T_prev);
+  float smx, smy, smz;
+  apply_rigid(cx.T, a.src_mean[0], a.src_mean[1], a.src_mean[2], smx, smy, smz);  // transform_ * src_mean_
+  cx.sm[0] = smx; cx.sm[1] = smy; cx.sm[2] = smz;
+  cx.dm[0] = a.dm[0]; cx.dm[1] = a.dm[1]; cx.dm[2] = a.dm[2];
+  cx.w_pt = a.w_pt;
+  cx.w_pl = a.w_pl;
+}
+
+constexpr int kWarmQpt = 4;                     // queries per thread and tile of the cached pass
+constexpr int kWarmTile = kWarmQpt * kBlock;    // queries per tile of the cached pass
+
+// ---- kernel 1 of a warm iteration: the cached pass ------------------------------------------------------------------
+// Elementwise over the source cloud, no search code, no shared-memory staging: per query 16 B (point) + 8 B (cache)
+// streamed and one 16 B gather of the cached match (+ 16 B normal for the plane term). Queries that pass the
+// exclusion test accumulate their pair here; the others are flagged in a bit mask (one word per 32 consecutive
+// queries) for the search kernel. PERSISTENT: the grid is a whole number of resident blocks per SM, a block walks
+// the tiles blockIdx.x, + gridDim.x, ... (static round-robin: every tile costs the same, and the assignment —
+// hence the summation order — is fixed), the next tile's streamed loads are in flight while the current tile is
+// evaluated, and the moments are reduced ONCE per block (a per-tile reduction cost as much as the tile itself).
+// The block rows go through the same deterministic grid reduction into rs.result + 32.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_constant__ LoopArgs a) {
+  constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
+  __shared__ BlockCtx cx;
+  __shared__ AsyncReduceSmem<NV> rsm;
+  const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t ntiles = (a.n_src + kWarmTile - 1) / kWarmTile;
+  // everything that does not depend on the loop state is requested before the state arrives
+  float4 s[kWarmQpt];
+  float r[kWarmQpt];
+  int seed[kWarmQpt];
+  auto stream_loads = [&](uint32_t tile) {
+#pragma unroll
+    for (int k = 0; k < kWarmQpt; k++) {
+      const uint32_t i = tile * kWarmTile + k * kBlock + tid;
+      const bool active = tile < ntiles && i < a.n_src;
+      s[k] = active ? __ldg(a.src_pts + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      r[k] = active ? __ldcg(a.cache_r + i) : 0.f;
+      seed[k] = active ? __ldcg(a.cache_pos + i) : -1;
+    }
+  };
+  stream_loads(blockIdx.x);
+  if (tid == 0) {
+    rsm.arrived = 0u;
+    load_block_ctx(a, cx);
+  }
+  __syncthreads();
+  if (cx.done) return;
+  if (a.trace && blockIdx.x == 0 && tid == 0) {
+    const int slot = __ldcg(&a.st->iters) & 63;
+    a.st->trace[slot][0] = global_timer_ns();
+    a.st->trace[slot][4] = 0ull;
+  }
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) acc[v] = 0.0;
+#pragma unroll 1
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t base = tile * kWarmTile;
+    float4 p[kWarmQpt], sc[kWarmQpt];
+    float rc[kWarmQpt];
+    int sd[kWarmQpt];
+#pragma unroll
+    for (int k = 0; k < kWarmQpt; k++) {
+      sc[k] = s[k];
+      rc[k] = r[k];
+      sd[k] = seed[k];
+      p[k] = (sd[k] >= 0 && rc[k] > 0.f) ? __ldg(a.dst.pts + sd[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    stream_loads(tile + gridDim.x);  // next tile of this block: in flight during the evaluation below
+#pragma unroll
+    for (int k = 0; k < kWarmQpt; k++) {
+      const uint32_t i = base + k * kBlock + tid;
+      const bool active = i < a.n_src;
+      bool miss = active;
+      if (active && rc[k] > 0.f) {
+        float qx, qy, qz, ox, oy, oz;
+        apply_rigid(cx.T, sc[k].x, sc[k].y, sc[k].z, qx, qy, qz);
+        apply_rigid(cx.Tp, sc[k].x, sc[k].y, sc[k].z, ox, oy, oz);
+        const float ex = __fsub_rn(qx, ox), ey = __fsub_rn(qy, oy), ez = __fsub_rn(qz, oz);
+        // upper bound of the distance the query moved since the previous iteration
+        const float dl = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex)))), kUp18);
+        const float r2 = __fsub_rd(rc[k], dl);
+        if (r2 > 0.f) {
+          // every reference point other than `seed` has a computed d2 above lim under the current transform
+          const float lim = __fmul_rd(__fmul_rd(r2, r2), kDown17);
+          bool pair = false;
+          if (sd[k] >= 0) {
+            const float dx = __fsub_rn(qx, p[k].x), dy = __fsub_rn(qy, p[k].y), dz = __fsub_rn(qz, p[k].z);
+            float d2 = __fmul_rn(dx, dx);
+            d2 = __fadd_rn(d2, __fmul_rn(dy, dy));
+            d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
+            if (d2 < a.max_d2) {
+              if (d2 < lim) {  // still the unique nearest neighbour, inside the radius
+                miss = false;
+                pair = true;
+              }
+            } else if (a.max_d2 <= lim) {  // the match left the radius and nothing else is inside it
+              miss = false;
+            }
+          } else if (a.max_d2 <= lim) {  // nothing was within the radius and nothing can have entered it
+            miss = false;
+          }
+          if (!miss) a.cache_r[i] = r2;
+          if (pair) {
+            const int pk = sd[k];
+            accumulate_pair<MODE, true>(
+                acc, cx, a.has_pt != 0, a.has_pl != 0, p[k], qx, qy, qz, a.src_nrm != nullptr,
+                [&] { return __ldg(a.dst.nrm + pk); }, [&] { return __ldg(a.src_nrm + i); });
+          }
+        }
+      }
+      const unsigned int mm = __ballot_sync(0xffffffffu, miss);
+      if (lane == 0 && (base + k * kBlock + (tid & ~31u)) < a.n_src) a.miss_mask[(base + k * kBlock + tid) >> 5] = mm;
+    }
+  }
+  double tot = 0;
+  if (!grid_reduce_async_tail<NV>(acc, a.rs, rsm, tot)) return;
+  if (lane < NV) a.rs.result[32 + lane] = tot;
+}
+
+#ifndef CB_LOOP_MIN_BLOCKS
+#define CB_LOOP_MIN_BLOCKS 5
+#endif
+
+// ---- kernel 2 of an iteration (the only one of a cold iteration): search + finish ------------------------------------------
+// kCold: nothing is cached, every query of the tile is searched (one 256-query chunk per block). Otherwise the
+// block compacts the flagged queries of its tile (kQpt x 256 queries) from the bit masks of the cached pass, in
+// ascending order, and dense warps search them. The searching thread accumulates its pair; the last warp of the
+// grid adds the cached pass's totals, all-reduces with the peers, solves, and writes the next transform.
+template <int MODE, int kQpt, bool kCold>
+__global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(const __grid_constant__ LoopArgs a) {
+  static_assert(!kCold || kQpt == 1, "a cold iteration searches one chunk per block");
+  constexpr int kTile = kQpt * kBlock;  // queries per block
+  constexpr int kWords = kTile / 32;    // mask words per tile
+  constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
+  __shared__ BlockCtx cx;
+  __shared__ WideSearchSmem wsm[kBlock / 32];
+  __shared__ AsyncReduceSmem<NV> rsm;
+  __shared__ unsigned short queue[kCold ? 1 : kTile];  // slots of the tile that need a search, ascending
+  __shared__ unsigned int smask[kWords], spre[kWords + 1];
+
+  const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t base = blockIdx.x * kTile;
+  unsigned int total = 0;
+  if (tid == 0) {
+    rsm.arrived = 0u;
+    load_block_ctx(a, cx);
+  }
+  if (!kCold) {
+    static_assert(kCold || kWords <= 32, "one warp scans the tile's mask words");
+    if (warp == 1) {  // (warp 0's first lane is busy with the state)
+      const uint32_t w = (base >> 5) + lane;
+      const unsigned int m = (lane < kWords && w * 32u < a.n_src) ? __ldcg(a.miss_mask + w) : 0u;
+      unsigned int inc = __popc(m);
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += t;
+      }
+      if (lane < kWords) {
+        smask[lane] = m;
+        spre[lane + 1] = inc;
+      }
+      if (lane == 0) spre[0] = 0u;
+    }
+  }
+  __syncthreads();
+  if (cx.done) return;  // converged (or failed) in an earlier launch of this batch
+  const int trace_slot = a.trace ? (__ldcg(&a.st->iters) & 63) : 0;
+  if (a.trace && blockIdx.x == 0 && tid == 0) {
+    a.st->trace[trace_slot][5] = global_timer_ns();
+    if (kCold) {
+      a.st->trace[trace_slot][0] = a.st->trace[trace_slot][5];
+      a.st->trace[trace_slot][4] = 0ull;
+    }
+  }
+  if (kCold) {
+    total = (base < a.n_src) ? min((uint32_t)kTile, a.n_src - base) : 0u;
+  } else {
+    total = spre[kWords];
+    if (total > 0) {  // block-uniform
+#pragma unroll
+      for (int k = 0; k < kQpt; k++) {
+        const unsigned int j = k * (kBlock / 32) + warp;  // mask word of slots k*256 + warp*32 .. +31
+        const unsigned int m = smask[j];
+        if ((m >> lane) & 1u) queue[spre[j] + __popc(m & ((1u << lane) - 1u))] = (unsigned short)(k * kBlock + tid);
+      }
+      __syncthreads();
+    }
+  }
+  if (a.trace && tid == 0 && total > 0) atomicAdd(&a.st->trace[trace_slot][4], (unsigned long long)total);
+  double tot = 0;
+  if (total == 0) {
+    // nothing to search in this tile (the usual case once the cache is warm): warp 0 contributes a zero row
+    if (warp != 0) return;
+    if (!grid_reduce_rows_tail<NV>(0.0, a.rs, (int)lane, tot)) return;
+  } else {
+    // ---- dense warps search the queued queries; the searching thread accumulates its pair ------------------------
+    double acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) acc[v] = 0.0;
+    if ((tid & ~31u) < total) {
+      const ChunkPair cp = search_chunk_body<kCold>(a, cx, &wsm[warp], queue, 0u, total, base);
+      if (cp.pos >= 0) {
+        const float4 dp = __ldg(a.dst.pts + cp.pos);
+        accumulate_pair<MODE, true>(
+            acc, cx, a.has_pt != 0, a.has_pl != 0, dp, cp.qx, cp.qy, cp.qz, a.src_nrm != nullptr,
+            [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); });
+      }
+    }
+    if constexpr (kQpt > 1) {
+#pragma unroll 1
+      for (unsigned int c = kBlock; c < total; c += kBlock) {
+        if (c + (tid & ~31u) >= total) break;  // warp-uniform; later chunks are empty for this warp too
+        ChunkPair cp;
+        search_chunk_far(&a, &cx, &wsm[warp], queue, c, total, base, &cp);
+        if (cp.pos >= 0) {
+          const float4 dp = __ldg(a.dst.pts + cp.pos);
+          accumulate_pair<MODE, true>(
+              acc, cx, a.has_pt != 0, a.has_pl != 0, dp, cp.qx, cp.qy, cp.qz, a.src_nrm != nullptr,
+              [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); });
+        }
+      }
+    }
+    // ---- reduction ----------------------------------------------------------------------------------------------------
+    if (!grid_reduce_async_tail<NV>(acc, a.rs, rsm, tot)) return;
+  }
+  // the last warp of the grid adds the cached pass, exchanges, solves and publishes the next transform
+  if (!kCold && lane < NV) tot += __ldcg(a.rs.result + 32 + lane);  // totals of the cached pass (fixed order: search + cached)
+  bool late = false;
+  if (a.trace && lane == 0) a.st->trace[trace_slot][1] = global_timer_ns();
+  const unsigned long long seq = __ldcg(&a.st->xseq) + 1ull;
+  if (a.rs.ex.enabled && a.rs.ex.world > 1) {
+    Exchange ex = a.rs.ex;
+    ex.seq = seq;  // executed passes are numbered on the device: launches skipped after convergence take no number
+    tot = exchange_rows<NV>(tot, ex, (int)lane, &late);
+  }
+  if (a.trace && lane == 0) a.st->trace[trace_slot][2] = global_timer_ns();
+  double* sbuf = rsm.slot[0];  // every warp of this block has arrived: the slots are free
+  if (lane < NV) sbuf[lane] = tot;
+  __syncwarp();
+  if (lane == 0) loop_solve<MODE>(&a, &cx, sbuf, late ? 1 : 0, seq);
+}
+
+}  // namespace
+
+int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
+  cb_context* ctx = icp->ctx;
+  const uint64_t launches0 = ctx->launches;
+  const int max_iter = std::max(prm->max_iter, 0);
+  const int timing = prm->timing;
+  if (!icp->d_state) {
+    CB_CUDA(cudaMalloc(&icp->d_state, sizeof(LoopState)));
+    CB_CUDA(cudaMallocHost(&icp->h_state, sizeof(LoopState)));
+  }
+  while (timing != 0 && (int)icp->events.size() < 2 * max_iter) {
+    cudaEvent_t e;
+    CB_CUDA(cudaEventCreate(&e));
+    icp->events.push_back(e);
+  }
+  const size_t ns = icp->src->n;
+  LoopArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.dst = grid_view(icp->dst);
+  a.src_pts = icp->src->d_pts;
+  a.src_nrm = (prm->metric == CB_ICP_COMBINED) ? icp->src->d_nrm : nullptr;
+  a.n_src = (uint32_t)ns;
+  a.max_d2 = prm->max_d2;
+  a.w_pt = prm->w_pt;
+  a.w_pl = prm->w_pl;
+  a.tol = prm->tol;
+  for (int r = 0; r < 3; r++) {
+    a.dm[r] = icp->dst_mean[r];
+    a.src_mean[r] = icp->src_mean[r];
+  }
+  const bool dst_has_normals = icp->dst->d_nrm != nullptr;
+  a.has_pt = prm->w_pt > 0.f;
+  a.has_pl = (prm->w_pl > 0.f) && dst_has_normals;
+  a.bail = (prm->w_pl > 0.f) && !dst_has_normals;
+  a.cache_pos = icp->d_nn_pos;
+  a.cache_r = icp->d_nn_d2;
+  {
+    // widening of a search beyond the nearest distance, in cell edges of the destination grid: first iteration
+    // (no motion known yet), floor and cap of 2 x (the query's last motion). CB_LOOP_SLACK="first,min,max".
+    float f[3] = {0.10f, 0.02f, 0.30f};
+    if (const char* e = getenv("CB_LOOP_SLACK")) sscanf(e, "%f,%f,%f", &f[0], &f[1], &f[2]);
+    const float h = 1.0f / a.dst.inv_h;
+    a.slack_first = f[0] * h;
+    a.slack_min = f[1] * h;
+    a.slack_max = f[2] * h;
+  }
+  a.st = icp->d_state;
+  static const bool trace = getenv("CB_LOOP_TRACE") != nullptr;
+  a.trace = trace ? 1 : 0;
+  // cold iteration (first launch: nothing cached): search kernel alone, one 256-query chunk per block; warm
+  // iterations: cached pass (kWarmTile queries per block) + search kernel over the flagged queries
+  const int blocks_cold = std::max(1, (int)((ns + kBlock - 1) / kBlock));
+  const int blocks_search = std::max(1, (int)((ns + (size_t)kQptWarm * kBlock - 1) / ((size_t)kQptWarm * kBlock)));
+  // persistent cached pass: a whole number of resident blocks per SM (never more blocks than tiles)
+  const int cached_per_sm = 2;  // __launch_bounds__ of icp_cached_kernel
+  const int blocks_cached = std::max(1, std::min(ctx->sm_count * cached_per_sm, (int)((ns + kWarmTile - 1) / kWarmTile)));
+  CB_TRY(get_reduce_scratch(ctx, blocks_cold, kMaxValues, &a.rs));
+  if (!icp->d_miss_mask) CB_CUDA(cudaMalloc(&icp->d_miss_mask, (ns / 32 + 2) * sizeof(uint32_t)));
+  a.miss_mask = icp->d_miss_mask;
+  Exchange ex;
+  std::memset(&ex, 0, sizeof(ex));
+  const bool fused = ctx->world > 1 && arm_exchange(ctx, &ex);  // tables + timeout; the pass number lives in LoopState
+  if (fused) ctx->seq -= 1;  // arm_exchange numbered a pass that is not issued here
+  if (ctx->world > 1 && !fused) {
+    set_error("the device-resident ICP loop needs the fused exchange (cb_comm_ipc_attach) when world > 1");
+    return CB_ERR_UNSUPPORTED;
+  }
+  a.rs.ex = ex;
+  ctx->pass_armed = false;
+
+  LoopState* hs = icp->h_state;
+  std::memset(hs, 0, sizeof(*hs));
+  std::memcpy(hs->T, prm->T_init, sizeof(hs->T));       // icp_base.hpp:71
+  std::memcpy(hs->T_prev, prm->T_init, sizeof(hs->T));
+  hs->last_delta = INFINITY;
+  hs->xseq = ctx->seq;
+  CB_CUDA(cudaMemcpyAsync(icp->d_state, hs, sizeof(*hs), cudaMemcpyHostToDevice, ctx->stream));
+
+  int issued = 0;
+  static const int kBatch = [] {
+    const char* e = getenv("CB_LOOP_BATCH");
+    return e ? std::max(1, atoi(e)) : 16;
+  }();
+  bool finished = (max_iter == 0);
+  while (!finished) {
+    const int n = std::min(kBatch, max_iter - issued);
+    for (int k = 0; k < n; ++k) {
+      if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
+      if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k)], ctx->stream));
+      const bool cold = (issued + k == 0);
+      if (prm->metric == CB_ICP_POINT_TO_POINT) {
+        if (cold) {
+          icp_search_kernel<kModeP2PCentered, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
+        } else {
+          icp_cached_kernel<kModeP2PCentered><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          icp_search_kernel<kModeP2PCentered, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
+        }
+      } else {
+        if (cold) {
+          icp_search_kernel<kModeCombined, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
+        } else {
+          icp_cached_kernel<kModeCombined><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          icp_search_kernel<kModeCombined, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
+        }
+      }
+      ctx->launches += cold ? 0 : 1;
+      ctx->launches += 1;
+      if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k) + 1], ctx->stream));
+    }
+    CB_CUDA(cudaGetLastError());
+    issued += n;
+    CB_CUDA(cudaMemcpyAsync(hs, icp->d_state, sizeof(*hs), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    finished = hs->done != 0 || issued >= max_iter;
+  }
+  if (max_iter == 0) CB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->seq = hs->xseq;
+  if (hs->done == 2) {
+    set_error("device-resident ICP loop: a peer rank did not deliver its row in time (rank %d of %d, iteration %d)",
+              ctx->rank, ctx->world, hs->iters);
+    ctx->ex_ready = false;
+    return hs->error ? hs->error : CB_ERR_NCCL;
+  }
+  const int iters = hs->iters;
+  if (trace) {
+    unsigned long long prev = 0;
+    for (int k = std::max(0, iters - 64); k < iters; ++k) {
+      const unsigned long long* t = hs->trace[k & 63];
+      fprintf(stderr, "[rank %d iteration %d] searched %llu of %zu queries; start->search kernel %.1f us, ->reduced %.1f us, ->peers %.1f us, ->solved %.1f us; period %.1f us\n",
+              ctx->rank, k, t[4], ns, (t[5] - t[0]) * 1e-3, (t[1] - t[5]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3,
+              prev ? (t[0] - prev) * 1e-3 : 0.0);
+      prev = t[0];
+    }
+  }
+  icp->iter_ms.assign(iters, 0.0);
+  double total = 0;
+  for (int k = 0; k < iters && timing != 0; k++) {
+    float ms = 0.f;
+    CB_CUDA(cudaEventElapsedTime(&ms, icp->events[2 * k], icp->events[2 * k + 1]));
+    icp->iter_ms[k] = ms;
+    total += ms;
+  }
+  icp->search_ms = total;
+  icp->nn_valid = iters > 0;
+  icp->nn_stored = false;  // d_nn_pos / d_nn_d2 hold the cache, not a per-query result list
+  icp->warm_ok = false;
+  icp->engine_last = false;
+  std::memcpy(icp->T_search, hs->T_prev, sizeof(icp->T_search));
+  icp->max_d2_search = prm->max_d2;
+  std::memcpy(res->T, hs->T, sizeof(res->T));
+  res->iterations = iters;
+  res->last_delta = hs->last_delta;
+  res->converged = hs->last_delta < prm->tol;
+  res->num_corr = (uint64_t)(hs->n_corr + 0.5);
+  res->gpu_ms_total = total;
+  res->gpu_ms_search = total;
+  res->kernel_launches = ctx->launches - launches0;
+  return CB_OK;
+}
+
+}  // namespace cb

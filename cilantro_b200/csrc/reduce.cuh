@@ -128,38 +128,60 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// Bit 63 of the host flag / of Exchange-level status words marks a pass whose peer wait timed out.
+constexpr unsigned long long kExchangeErrBit = 1ull << 63;
+
+// Steps 1-3 of the fused all-reduce: lane i < NV holds this GPU's total of value i; returns the cross-rank total
+// (rows summed in rank order: bit-identical on every rank). The wait for the peers' rows is BOUNDED: if a peer's
+// row of this pass has not landed within ex.timeout_ns (a rank that died, never launched its pass, or was
+// configured differently), *timed_out is set on every lane and the value returned is meaningless - the caller
+// reports the failure (host mailbox flag with kExchangeErrBit / error state of the device loop) instead of
+// spinning forever.
+template <int NV>
+__device__ __forceinline__ double exchange_rows(double s, const Exchange& ex, int lane, bool* timed_out) {
+  const int par = (int)(ex.seq & 1ull);
+  bool late = false;
+  // 1. my row -> every rank's table (remote stores over NVLink), then a release flag per rank
+  if (lane < NV)
+    for (int p = 0; p < ex.world; ++p) ex.peer_vals[p][(par * ex.world + ex.rank) * kExchangeVals + lane] = s;
+  __threadfence_system();
+  __syncwarp();
+  if (lane < ex.world) st_release_sys(ex.peer_flags[lane] + par * ex.world + ex.rank, ex.seq);
+  // 2. wait until every rank's row of THIS pass has landed in my table (lane r watches rank r)
+  if (lane < ex.world) {
+    const unsigned long long* f = ex.peer_flags[ex.rank] + par * ex.world + lane;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (ld_acquire_sys(f) != ex.seq) {
+      if ((++spins & 0xffu) == 0u && ex.timeout_ns != 0ull && global_timer_ns() - t0 > ex.timeout_ns) {
+        late = true;
+        break;
+      }
+    }
+  }
+  late = __any_sync(0xffffffffu, late);
+  // 3. identical fixed-order sum on every rank -> bit-identical totals, no broadcast needed
+  if (!late && lane < NV) {
+    const volatile double* rows = ex.peer_vals[ex.rank] + (size_t)par * ex.world * kExchangeVals;
+    s = 0;
+    for (int r = 0; r < ex.world; ++r) s += rows[r * kExchangeVals + lane];
+  }
+  *timed_out = late;
+  return s;
+}
+
 template <int NV>
 __device__ __forceinline__ double exchange_and_publish(double s, const ReduceScratch& rs, int lane) {
   const Exchange& ex = rs.ex;
   if (ex.enabled) {
-    const int par = (int)(ex.seq & 1ull);
+    bool late = false;
     if (ex.trace && lane == 0) ex.trace[1] = global_timer_ns();  // local reduction done
-    if (ex.world > 1) {
-      // 1. my row -> every rank's table (remote stores over NVLink), then a release flag per rank
-      if (lane < NV)
-        for (int p = 0; p < ex.world; ++p) ex.peer_vals[p][(par * ex.world + ex.rank) * kExchangeVals + lane] = s;
-      __threadfence_system();
-      __syncwarp();
-      if (lane < ex.world) st_release_sys(ex.peer_flags[lane] + par * ex.world + ex.rank, ex.seq);
-      // 2. wait until every rank's row of THIS pass has landed in my table (lane r watches rank r)
-      if (lane < ex.world) {
-        const unsigned long long* f = ex.peer_flags[ex.rank] + par * ex.world + lane;
-        while (ld_acquire_sys(f) != ex.seq) {
-        }
-      }
-      __syncwarp();
-      // 3. identical fixed-order sum on every rank -> bit-identical totals, no broadcast needed
-      if (lane < NV) {
-        const volatile double* rows = ex.peer_vals[ex.rank] + (size_t)par * ex.world * kExchangeVals;
-        s = 0;
-        for (int r = 0; r < ex.world; ++r) s += rows[r * kExchangeVals + lane];
-      }
-    }
+    if (ex.world > 1) s = exchange_rows<NV>(s, ex, lane, &late);
     if (ex.trace && lane == 0) ex.trace[2] = global_timer_ns();  // peers' rows received and summed
     if (lane < NV) ex.host_vals[lane] = s;
     __threadfence_system();
     __syncwarp();
-    if (lane == 0) st_release_sys(ex.host_flag, ex.seq);
+    if (lane == 0) st_release_sys(ex.host_flag, late ? (ex.seq | kExchangeErrBit) : ex.seq);
     if (ex.trace && lane == 0) ex.trace[3] = global_timer_ns();  // host mailbox flag written
   }
   return s;
@@ -188,14 +210,51 @@ __device__ __forceinline__ double warp_transpose_reduce(double (&v)[NP], int lan
   return v[0];
 }
 
+// Group / grid levels of the barrier-free reduction, entered by ONE warp per block with lane i < NV holding value i
+// of the block's row (a block with nothing to add passes zeros: its row must exist, the folds read every row).
+// Returns true on exactly one warp of the grid - the last to arrive - with `tot` = this GPU's total of value `lane`.
 template <int NV>
-__device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const ReduceScratch& rs, AsyncReduceSmem<NV>& sm) {
+__device__ __forceinline__ bool grid_reduce_rows_tail(double row, const ReduceScratch& rs, int lane, double& tot) {
+  unsigned int t = 0;
+  if (lane < NV) rs.partials[(size_t)blockIdx.x * NV + lane] = row;
+  const unsigned int ngroups = (gridDim.x + kReduceGroup - 1) / kReduceGroup;
+  const unsigned int g = blockIdx.x / kReduceGroup;
+  const unsigned int g0 = g * kReduceGroup, g1 = min(gridDim.x, g0 + kReduceGroup);
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) t = atomicAdd(rs.counters + 1 + g, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != (g1 - g0) - 1) return false;
+  __threadfence();
+  {
+    const double gs = warp_sum_rows<NV>(rs.partials, g0, g1, lane);
+    if (lane < NV) rs.gpartials[(size_t)g * NV + lane] = gs;
+  }
+  if (lane == 0) rs.counters[1 + g] = 0;
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) t = atomicAdd(rs.counters, 1u);
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != ngroups - 1) return false;
+  __threadfence();
+  // the last warp of the grid: this GPU's totals
+  tot = warp_sum_rows<NV>(rs.gpartials, 0, ngroups, lane);
+  if (lane == 0) rs.counters[0] = 0;
+  return true;
+}
+
+// Returns true on exactly ONE warp of the grid - the last to arrive - with `tot` = this GPU's total of value
+// `lane` (lane < NV); every other warp returns false as soon as its part is done. The caller continues alone on
+// that warp (exchange, publication, the device-resident solve of icp_loop.cu).
+template <int NV>
+__device__ __forceinline__ bool grid_reduce_async_tail(double (&acc)[NV], const ReduceScratch& rs, AsyncReduceSmem<NV>& sm,
+                                                       double& tot) {
   static_assert(NV <= 32, "one lane per value");
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int kWarps = kReduceBlock / 32;
   if constexpr (NV == 16) {
-    const double tot = warp_transpose_reduce<16>(acc, lane);
-    if ((lane & 1) == 0) sm.slot[warp][lane >> 1] = tot;
+    const double t16 = warp_transpose_reduce<16>(acc, lane);
+    if ((lane & 1) == 0) sm.slot[warp][lane >> 1] = t16;
   } else {
 #pragma unroll
     for (int i = 0; i < NV; i++) {
@@ -212,39 +271,23 @@ __device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const Reduc
     t = atomicAdd(&sm.arrived, 1u);
   }
   t = __shfl_sync(0xffffffffu, t, 0);
-  if (t != kWarps - 1) return;
+  if (t != kWarps - 1) return false;
   __threadfence_block();
   // last warp of the block: block row
+  double row = 0;
   if (lane < NV) {
-    double s = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) s += ((volatile double*)sm.slot[w])[lane];
-    rs.partials[(size_t)blockIdx.x * NV + lane] = s;
+    for (int w = 0; w < kWarps; w++) row += ((volatile double*)sm.slot[w])[lane];
   }
-  const unsigned int ngroups = (gridDim.x + kReduceGroup - 1) / kReduceGroup;
-  const unsigned int g = blockIdx.x / kReduceGroup;
-  const unsigned int g0 = g * kReduceGroup, g1 = min(gridDim.x, g0 + kReduceGroup);
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) t = atomicAdd(rs.counters + 1 + g, 1u);
-  t = __shfl_sync(0xffffffffu, t, 0);
-  if (t != (g1 - g0) - 1) return;
-  __threadfence();
-  {
-    const double gs = warp_sum_rows<NV>(rs.partials, g0, g1, lane);
-    if (lane < NV) rs.gpartials[(size_t)g * NV + lane] = gs;
-  }
-  if (lane == 0) rs.counters[1 + g] = 0;
-  __threadfence();
-  __syncwarp();
-  if (lane == 0) t = atomicAdd(rs.counters, 1u);
-  t = __shfl_sync(0xffffffffu, t, 0);
-  if (t != ngroups - 1) return;
-  __threadfence();
-  // the last warp of the grid: this GPU's totals -> (optional) fused all-reduce over NVLink peer
-  // memory -> device result + mapped host mailbox
-  double tot = warp_sum_rows<NV>(rs.gpartials, 0, ngroups, lane);
-  if (lane == 0) rs.counters[0] = 0;
+  return grid_reduce_rows_tail<NV>(row, rs, lane, tot);
+}
+
+// ... -> (optional) fused all-reduce over NVLink peer memory -> device result + mapped host mailbox
+template <int NV>
+__device__ __forceinline__ void grid_reduce_async(double (&acc)[NV], const ReduceScratch& rs, AsyncReduceSmem<NV>& sm) {
+  const int lane = threadIdx.x & 31;
+  double tot = 0;
+  if (!grid_reduce_async_tail<NV>(acc, rs, sm, tot)) return;
   tot = exchange_and_publish<NV>(tot, rs, lane);
   if (lane < NV) rs.result[lane] = tot;
 }

@@ -144,6 +144,78 @@ CB_HD Mat3 rotation_from_svd(const Svd& s, int flip_col) {
   return mul(U, transpose(s.V));
 }
 
+// Orthogonal polar factor Q = U V^T of A = U S V^T by Newton's iteration X <- (mu X + X^-T / mu) / 2 (Frobenius
+// scaling in the first steps), for the common case det(A) > 0 and A not close to singular: then Q is a proper
+// rotation and equals what both SVD-based rules of rotation_from_svd() return (no reflection to repair), at a
+// fraction of the serial latency of a Jacobi SVD (one division per step instead of several divisions and square
+// roots per plane rotation) - it runs in the single-thread epilogue of every device-resident ICP iteration.
+// Returns false (Q untouched) when A has det <= 0 or sigma_2 sigma_3 / sigma_1^2 < ~1e-6: the callers then take
+// the SVD path, which also owns the reflection and rank-deficient rules.
+CB_HD bool polar_rotation(const Mat3& A, Mat3& Q) {
+  double f2 = 0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) f2 += A.m[i][j] * A.m[i][j];
+  if (!(f2 > 0.0) || !(f2 < 1e300)) return false;
+  const double d0 = det(A);
+  if (!(d0 > 1e-6 * f2 * sqrt(f2))) return false;
+  Mat3 X = A;
+  for (int k = 0; k < 40; ++k) {
+    // cofactor matrix C (X^-T = C / det X)
+    Mat3 C;
+    C.m[0][0] = X.m[1][1] * X.m[2][2] - X.m[1][2] * X.m[2][1];
+    C.m[0][1] = X.m[1][2] * X.m[2][0] - X.m[1][0] * X.m[2][2];
+    C.m[0][2] = X.m[1][0] * X.m[2][1] - X.m[1][1] * X.m[2][0];
+    C.m[1][0] = X.m[0][2] * X.m[2][1] - X.m[0][1] * X.m[2][2];
+    C.m[1][1] = X.m[0][0] * X.m[2][2] - X.m[0][2] * X.m[2][0];
+    C.m[1][2] = X.m[0][1] * X.m[2][0] - X.m[0][0] * X.m[2][1];
+    C.m[2][0] = X.m[0][1] * X.m[1][2] - X.m[0][2] * X.m[1][1];
+    C.m[2][1] = X.m[0][2] * X.m[1][0] - X.m[0][0] * X.m[1][2];
+    C.m[2][2] = X.m[0][0] * X.m[1][1] - X.m[0][1] * X.m[1][0];
+    const double dx = X.m[0][0] * C.m[0][0] + X.m[0][1] * C.m[0][1] + X.m[0][2] * C.m[0][2];
+    if (!(dx > 0.0)) return false;
+    const double rdx = 1.0 / dx;  // the only double-precision division of a step
+    double a = 0.5, b = 0.5 * rdx;  // X <- a X + b C
+    if (k < 2) {
+      // Frobenius scaling mu = (|X^-T|_F / |X|_F)^(1/2) speeds up the first steps when A is far from orthogonal.
+      // Any positive mu gives a valid step (the unscaled steps k >= 2 decide the limit), so single precision is
+      // enough: mu^4 = |C|^2 / (det^2 |X|^2)
+      double fx = 0, fc = 0;
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+          fx += X.m[i][j] * X.m[i][j];
+          fc += C.m[i][j] * C.m[i][j];
+        }
+      const float mu4 = (float)(fc * rdx * rdx) / (float)fx;
+      if (mu4 > 1e-30f && mu4 < 1e30f) {
+        const float mu = sqrtf(sqrtf(mu4));
+        a = 0.5 * (double)mu;
+        b = 0.5 * rdx * (double)(1.0f / mu);
+      }
+    }
+    double diff = 0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const double xn = a * X.m[i][j] + b * C.m[i][j];
+        const double e = xn - X.m[i][j];
+        diff += e * e;
+        X.m[i][j] = xn;
+      }
+    if (k >= 2 && diff < 1e-28) {  // quadratic convergence: a step of 1e-14 leaves an error of ~1e-28
+      Q = X;
+      return true;
+    }
+  }
+  return false;
+}
+
+// U V^T of A with the reflection rule of rotation_from_svd(.., flip_col): the polar iteration when it applies,
+// else the Jacobi SVD.
+CB_HD Mat3 nearest_rotation(const Mat3& A, int flip_col) {
+  Mat3 Q;
+  if (polar_rotation(A, Q)) return Q;
+  return rotation_from_svd(svd_hestenes(A), flip_col);
+}
+
 // Solve the 6x6 system A x = b (A symmetric, given full row-major). Returns false when singular
 // to working precision (x is then the least-damaged elimination result, like a failed LDLT).
 CB_HD bool solve6(const double* A_in, const double* b_in, double* x) {
@@ -154,6 +226,7 @@ CB_HD bool solve6(const double* A_in, const double* b_in, double* x) {
     M[i][n] = b_in[i];
   }
   bool ok = true;
+  double rp[6];  // reciprocal pivots (one division per column; the back substitution re-uses them)
   for (int k = 0; k < n; k++) {
     int piv = k;
     for (int i = k + 1; i < n; i++)
@@ -167,10 +240,12 @@ CB_HD bool solve6(const double* A_in, const double* b_in, double* x) {
     const double d = M[k][k];
     if (d == 0.0 || !(d == d)) {
       ok = false;
+      rp[k] = 0.0;
       continue;
     }
+    rp[k] = 1.0 / d;
     for (int i = k + 1; i < n; i++) {
-      const double f = M[i][k] / d;
+      const double f = M[i][k] * rp[k];
       if (f == 0.0) continue;
       for (int j = k; j <= n; j++) M[i][j] -= f * M[k][j];
     }
@@ -178,7 +253,7 @@ CB_HD bool solve6(const double* A_in, const double* b_in, double* x) {
   for (int i = n - 1; i >= 0; i--) {
     double s = M[i][n];
     for (int j = i + 1; j < n; j++) s -= M[i][j] * x[j];
-    x[i] = (M[i][i] != 0.0) ? s / M[i][i] : 0.0;
+    x[i] = s * rp[i];
   }
   return ok;
 }
@@ -203,16 +278,16 @@ CB_HD bool kabsch_from_moments(const double* s, const float* pd, const float* pq
     t34_identity(T);
     return false;
   }
+  const double inv_n = 1.0 / n;
   double mud[3], muq[3];
   for (int r = 0; r < 3; r++) {
-    mud[r] = s[1 + r] / n;
-    muq[r] = s[4 + r] / n;
+    mud[r] = s[1 + r] * inv_n;
+    muq[r] = s[4 + r] * inv_n;
   }
   la::Mat3 sigma;
   for (int r = 0; r < 3; r++)
-    for (int c = 0; c < 3; c++) sigma.m[r][c] = s[7 + r * 3 + c] / n - mud[r] * muq[c];
-  const la::Svd svd = la::svd_hestenes(sigma);
-  const la::Mat3 R = la::rotation_from_svd(svd, 2);
+    for (int c = 0; c < 3; c++) sigma.m[r][c] = s[7 + r * 3 + c] * inv_n - mud[r] * muq[c];
+  const la::Mat3 R = la::nearest_rotation(sigma, 2);
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 3; c++) T[r * 4 + c] = (float)R.m[r][c];
   for (int r = 0; r < 3; r++) {
@@ -242,8 +317,10 @@ CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout,
   const double na = sqrt((double)dth[0] * dth[0] + (double)dth[1] * dth[1] + (double)dth[2] * dth[2]);
   const double theta = atan(na);
   double ax[3] = {0, 0, 0};
-  if (na > 0.0)
-    for (int i = 0; i < 3; i++) ax[i] = dth[i] / na;
+  if (na > 0.0) {
+    const double rna = 1.0 / na;
+    for (int i = 0; i < 3; i++) ax[i] = dth[i] * rna;
+  }
   const double c = cos(theta), sn = sin(theta), k1 = 1.0 - c;
   la::Mat3 Ra;
   for (int i = 0; i < 3; i++)
@@ -290,7 +367,7 @@ CB_HD void reorthonormalize(float* T) {
   la::Mat3 A;
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) A.m[i][j] = T[i * 4 + j];
-  const la::Mat3 R = la::rotation_from_svd(la::svd_hestenes(A), 0);
+  const la::Mat3 R = la::nearest_rotation(A, 0);
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) T[i * 4 + j] = (float)R.m[i][j];
 }

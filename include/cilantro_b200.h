@@ -208,7 +208,8 @@ typedef struct cb_icp_params {
   int32_t search_dir;          /* cb_search_dir; default CB_SECOND_TO_FIRST */
   int32_t require_reciprocal;  /* with CB_BOTH: intersection instead of union (:68-70 of ..._utilities.hpp) */
   int32_t one_to_one;          /* keep, per dst (SECOND_TO_FIRST) / src (FIRST_TO_SECOND) point, the closest pair */
-  int32_t reserved_;
+  int32_t host_loop;           /* 0 (default): iterations run back to back on the device where the configuration allows it
+                                  (default engine, one Gauss-Newton step per iteration); 1: host-driven loop (A/B, tests) */
   double inlier_fraction;      /* keep the llround(fraction * M) closest pairs when 0 < fraction < 1; default 1 */
 } cb_icp_params;
 
