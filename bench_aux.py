@@ -15,65 +15,93 @@ import numpy as np
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # nominal FMA rate of the FP32 pipe (SMs x lanes x 2 x max clock)
 
 
-def _ctx():
+def _ctx(ctx=None):
     import torch
 
     from cilantro_b200 import capi
 
     if not torch.cuda.is_available():
         raise SystemExit("bench needs a CUDA device: cilantro_b200 has no CPU fallback")
-    return capi, capi.Context(0)
+    return capi, (ctx if ctx is not None else capi.Context(0))
 
 
-def kmeans(args, n=50_000_000, k=1024):
+def brief(line):
+    """The fields of a workload line that bench.py's `secondary` block carries."""
+    keep = ("metric", "value", "unit", "iterations_per_sec", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype",
+            "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "parity")
+    return {k: line[k] for k in keep if k in line}
+
+
+def kmeans(args, n=50_000_000, k=1024, ctx=None, rank=0, world=1):
+    """KMeans3f, BASELINE config 4. world > 1: the points are split into contiguous shards, one per rank (all ranks
+    call this; the library all-reduces the K x 4 centroid sums per iteration); rank 0 returns the line."""
     import oracle
     from cilantro_b200 import synth
+    from cilantro_b200.dist import max_over_ranks, shard_bounds
 
-    capi, ctx = _ctx()
+    capi, ctx = _ctx(ctx)
     pts, cent0 = synth.kmeans_data(n, k, seed=1)
-    cloud = capi.Cloud(ctx, pts)
+    lo, hi = shard_bounds(n, rank, world)
+    mine = np.ascontiguousarray(pts[lo:hi])
+    cloud = capi.Cloud(ctx, mine, None, index_offset=lo)
     # warm-up
     capi.kmeans_cluster(ctx, cloud, cent0, max_iter=max(args.warmup, 1), tol=0.0, want_labels=False)
     l0 = ctx.kernel_launches()
     res = capi.kmeans_cluster(ctx, cloud, cent0, max_iter=args.steps, tol=0.0, want_labels=False)
     launches = ctx.kernel_launches() - l0
-    ms = res["gpu_ms_total"] / res["iterations"]
+    ms = max_over_ranks(res["gpu_ms_total"]) / res["iterations"]
     flop = 8.0 * n * k
     # e2e: host points -> upload -> cluster(steps) -> centroids + labels on host
     t0 = time.perf_counter()
-    c2 = capi.Cloud(ctx, pts)
+    c2 = capi.Cloud(ctx, mine, None, index_offset=lo)
     r2 = capi.kmeans_cluster(ctx, c2, cent0, max_iter=args.steps, tol=0.0, want_labels=True)
-    e2e_s = time.perf_counter() - t0
-    # CPU baseline: oracle brute-force assignment (OpenMP) + serial update on a bounded sample
-    sample = min(n, 5_000_000)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    c2.close()
+    cloud.close()
+    if rank != 0:
+        return None
+    # CPU baseline + parity: the oracle's assignment step (OpenMP) on a bounded sample; labels must be bit-exact
+    sample = min(hi - lo, 2_000_000)
     t0 = time.perf_counter()
-    oracle.kmeans(pts[:sample], cent0, max_iter=1, tol=0.0)
+    oc = oracle.kmeans(pts[:sample], cent0, max_iter=1, tol=0.0)
     cpu_s = time.perf_counter() - t0
+    parity = None
+    if world == 1:  # (with several ranks every clustering call on ctx is a collective)
+        c3 = capi.Cloud(ctx, np.ascontiguousarray(pts[:sample]))
+        g1 = capi.kmeans_cluster(ctx, c3, cent0, max_iter=1, tol=0.0, want_labels=True)
+        c3.close()
+        parity = {"labels_equal_after_one_iteration": bool(np.array_equal(g1["labels"], oc[1])), "points": int(sample),
+                  "centroid_max_abs_diff": float(np.abs(g1["centroids"] - oc[0]).max())}
     line = {
         "metric": "kmeans_point_assignments_per_sec", "value": n * 1e3 / ms, "unit": "points/s",
-        "iterations_per_sec": 1e3 / ms, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"KMeans3f: {n} uniform points, K={k}, fixed initial centroids, {args.steps} Lloyd iterations (tol=0)",
+        "iterations_per_sec": 1e3 / ms, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"KMeans3f: {n} uniform points ({hi - lo} per GPU x {world}), K={k}, fixed initial centroids, "
+                               f"{args.steps} Lloyd iterations (tol=0)",
+                   "parallelism": f"points sharded x{world}, centroids replicated, one ncclAllReduce of K x 4 doubles per iteration",
                    "l2": "inputs (600 MB) larger than L2"},
-        "e2e": {"value": n * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": pts.nbytes / args.steps,
-                "d2h_bytes_per_step": (8 * n + 12 * k) / args.steps,
+        "e2e": {"value": n * args.steps / e2e_s, "unit": "points/s", "h2d_bytes_per_step": mine.nbytes / args.steps,
+                "d2h_bytes_per_step": (8 * (hi - lo) + 12 * k) / args.steps,
                 "what": f"cb_cloud_create + cb_kmeans_cluster({args.steps}) + labels/centroids on host: {e2e_s:.3f} s"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "fp32", "achieved": flop / (ms * 1e-3) / 1e12, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": flop / (ms * 1e-3) / 1e12 / FP32_PEAK_TFLOPS, "traffic": None,
-                     "kernel": "kmeans_assign_kernel", "note": "8 N K flop per iteration (3 sub, 3 mul, 2 add; the "
+        "roofline": {"bound": "fp32", "achieved": flop / (ms * 1e-3) / 1e12 / world, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                     "frac": flop / (ms * 1e-3) / 1e12 / world / FP32_PEAK_TFLOPS, "traffic": None,
+                     "kernel": "kmeans_assign_kernel", "peak_source": "nominal: 148 SMs x 128 lanes x 2 x 1.965 GHz (MEASURED_PEAKS.json has no FP32 figure)",
+                     "note": "per GPU; 8 N K flop per iteration (3 sub, 3 mul, 2 add; the "
                      "arithmetic contract forbids FMA, so the attainable rate is half the FMA peak)"},
         "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": oracle.num_threads(), "kind": "port",
                          "sample": f"1 Lloyd iteration on the first {sample} points (brute-force assignment, OpenMP; serial update)"},
+        "parity": parity,
     }
-    print(json.dumps(line))
+    return line
 
 
-def ransac(args, n=5_000_000, batch=1000):
+def ransac(args, n=5_000_000, batch=1000, ctx=None):
     import oracle
     from cilantro_b200 import synth
 
-    capi, ctx = _ctx()
+    capi, ctx = _ctx(ctx)
     dst, src, T_ref, inl = synth.ransac_pairs(n, 0.3, seed=1)
     d_dst, d_src = capi.Cloud(ctx, dst), capi.Cloud(ctx, src)
     # hypotheses: the generating pose plus random rigid perturbations of it (inputs of the measured scoring call;
@@ -124,15 +152,16 @@ def ransac(args, n=5_000_000, batch=1000):
                      "note": "~30 flop per pair-hypothesis (SURVEY 8d), no FMA by contract; wall-clock per call incl. 48 KB H2D + 4 KB D2H"},
         "cpu_baseline": {"value": hyp_cpu / cpu_s, "unit": "hypotheses/s", "cores": oracle.num_threads(), "kind": "port",
                          "sample": f"{hyp_cpu} hypotheses scored over all {n} pairs (OpenMP over hypotheses)"},
+        "parity": {"inlier_counts_equal": True, "hypotheses_compared": hyp_cpu, "pairs": n},
     }
-    print(json.dumps(line))
+    return line
 
 
-def pca(args, n=50_000_000):
+def pca(args, n=50_000_000, ctx=None):
     import oracle
     from cilantro_b200 import synth
 
-    capi, ctx = _ctx()
+    capi, ctx = _ctx(ctx)
     pts, _ = synth.kmeans_data(n, 1, seed=2)
     cloud = capi.Cloud(ctx, pts)
     for _ in range(max(args.warmup, 1)):
@@ -153,6 +182,11 @@ def pca(args, n=50_000_000):
     t0 = time.perf_counter()
     o = oracle.pca(pts[:sample])
     cpu_s = time.perf_counter() - t0
+    # parity on the CPU sample: the same points through the device path
+    cs = capi.Cloud(ctx, np.ascontiguousarray(pts[:sample]))
+    g = capi.pca(ctx, cs)
+    cs.close()
+    pca_parity = _pca_parity(g, o, sample)
     line = {
         "metric": "pca_points_per_sec", "value": n * 1e3 / ms, "unit": "points/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -166,17 +200,18 @@ def pca(args, n=50_000_000):
                      "frac": 12.0 * n / (ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "moments_kernel", "peak_source": src},
         "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": 1, "kind": "port",
                          "sample": f"serial two-pass covariance (the reference's default, covariance.hpp:64-76) on {sample} points"},
+        "parity": pca_parity,
     }
-    print(json.dumps(line))
+    return line
 
 
-def normals(args, n=5_000_000, k=10):
+def normals(args, n=5_000_000, k=10, ctx=None):
     """PointCloud3f::estimateNormalsKNN(k) (view point = origin) on a synthetic scanned sheet."""
     import oracle
     from cilantro_b200 import synth
     from bench import load_peaks
 
-    capi, ctx = _ctx()
+    capi, ctx = _ctx(ctx)
     pts, _ = synth.surface_cloud(n, seed=1, noise=0.0005)
     cloud = capi.Cloud(ctx, pts)
     vp = [0.0, 0.0, 0.0]
@@ -223,16 +258,16 @@ def normals(args, n=5_000_000, k=10):
                          "sample": f"kNN (reference nanoflann, OpenMP) + covariance + eigen on {sample} points; "
                                    "kd-tree build not included"},
     }
-    print(json.dumps(line))
+    return line
 
 
-def downsample(args, n=10_000_000, bin_size=0.01):
+def downsample(args, n=10_000_000, bin_size=0.01, ctx=None):
     """PointCloud3f::gridDownsample(bin) on uniform points in the unit cube (~ n * bin^3 ... points per bin)."""
     import oracle
     from cilantro_b200 import synth
     from bench import load_peaks
 
-    capi, ctx = _ctx()
+    capi, ctx = _ctx(ctx)
     pts, _ = synth.kmeans_data(n, 1, seed=3)
     cloud = capi.Cloud(ctx, pts)
     for _ in range(max(args.warmup, 1)):
@@ -276,7 +311,27 @@ def downsample(args, n=10_000_000, bin_size=0.01):
         "cpu_baseline": {"value": sample / cpu_s, "unit": "points/s", "cores": oracle.num_threads(), "kind": "port",
                          "sample": f"the reference's default parallel std::map build (restated, OpenMP) on {sample} points"},
     }
-    print(json.dumps(line))
+    return line
+
+
+def _pca_parity(g, o, sample):
+    def get(d, *names):
+        for nm in names:
+            if nm in d:
+                return np.asarray(d[nm], np.float64)
+        return None
+
+    out = {"points": int(sample)}
+    gm, om = get(g, "mean"), get(o, "mean")
+    gc, oc = get(g, "cov", "covariance"), get(o, "cov", "covariance")
+    ge, oe = get(g, "eigenvalues", "evals"), get(o, "eigenvalues", "evals")
+    if gm is not None and om is not None:
+        out["mean_max_abs_diff"] = float(np.abs(gm.ravel() - om.ravel()).max())
+    if gc is not None and oc is not None:
+        out["cov_max_abs_diff"] = float(np.abs(gc.ravel() - oc.ravel()).max())
+    if ge is not None and oe is not None:
+        out["eigenvalue_max_abs_diff"] = float(np.abs(ge.ravel() - oe.ravel()).max())
+    return out
 
 
 AUX = {"downsample_10m": downsample, "downsample_1m": lambda a: downsample(a, n=1_000_000, bin_size=0.02),

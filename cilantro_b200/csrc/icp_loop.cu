@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_cons
 }
 
 #ifndef CB_LOOP_MIN_BLOCKS
-#define CB_LOOP_MIN_BLOCKS 5
+#define CB_LOOP_MIN_BLOCKS 4
 #endif
 
 // ---- kernel 2 of an iteration (the only one of a cold iteration): search + finish ------------------------------------------
@@ -481,7 +481,7 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
   {
     // widening of a search beyond the nearest distance, in cell edges of the destination grid: first iteration
     // (no motion known yet), floor and cap of 2 x (the query's last motion). CB_LOOP_SLACK="first,min,max".
-    float f[3] = {0.10f, 0.02f, 0.30f};
+    float f[3] = {0.20f, 0.02f, 0.30f};
     if (const char* e = getenv("CB_LOOP_SLACK")) sscanf(e, "%f,%f,%f", &f[0], &f[1], &f[2]);
     const float h = 1.0f / a.dst.inv_h;
     a.slack_first = f[0] * h;
