@@ -39,7 +39,17 @@ class IcpParams(C.Structure):
         ("one_to_one", C.c_int32),
         ("host_loop", C.c_int32),
         ("inlier_fraction", C.c_double),
+        ("pt_weight_kind", C.c_int32),
+        ("pl_weight_kind", C.c_int32),
+        ("pt_weight_coeff", C.c_float),
+        ("pl_weight_coeff", C.c_float),
     ]
+
+
+def rbf_coeff(sigma):
+    """RBFKernelWeightEvaluator's coefficient, in float like the reference: -(0.5f) / (sigma * sigma)."""
+    sg = np.float32(sigma)
+    return float(np.float32(-0.5) / (sg * sg))
 
 
 SEARCH_DIR = {"second_to_first": 0, "first_to_second": 1, "both": 2}
@@ -73,7 +83,7 @@ class RansacResult(C.Structure):
     ]
 
 
-# every symbol include/cilantro_b200.h declares (tests/test_capi_symbols.py checks the .so exports them)
+# every symbol include/cilantro_b200.h declares (tests/test_capi_host.py checks that the .so exports them and that this list matches the header)
 EXPORTED = [
     "cb_last_error", "cb_version",
     "cb_context_create", "cb_context_destroy", "cb_context_synchronize", "cb_context_device_info",
@@ -84,7 +94,7 @@ EXPORTED = [
     "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
     "cb_knn1_radius", "cb_knn_radius", "cb_radius_search", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
-    "cb_icp_correspondences", "cb_icp_residuals", "cb_icp_accumulate",
+    "cb_icp_correspondences", "cb_icp_residuals", "cb_icp_accumulate", "cb_icp_loop_cache",
     "cb_solve_kabsch_moments", "cb_solve_gauss_newton", "cb_solve_rotation", "cb_compose",
     "cb_kmeans_cluster", "cb_kmeans_assign", "cb_kmeans_seed_indices",
     "cb_ransac_score", "cb_ransac_residuals", "cb_ransac_rigid",
@@ -366,7 +376,7 @@ def transform_points(ctx, T, xyz):
 
 def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5,
                T_init=None, flush_l2=False, timing=1, search_dir="second_to_first", inlier_fraction=1.0,
-               require_reciprocal=False, one_to_one=False, host_loop=False):
+               require_reciprocal=False, one_to_one=False, host_loop=False, pt_rbf_sigma=None, pl_rbf_sigma=None):
     p = IcpParams()
     lib().cb_icp_default_params(C.byref(p))
     p.metric = 0 if metric == "p2p" else 1
@@ -386,6 +396,10 @@ def icp_params(metric="p2p", max_iter=15, tol=1e-5, max_d2=1e-4, w_pt=0.0, w_pl=
     p.require_reciprocal = int(require_reciprocal)
     p.one_to_one = int(one_to_one)
     p.host_loop = int(host_loop)
+    if pt_rbf_sigma is not None:
+        p.pt_weight_kind, p.pt_weight_coeff = 1, rbf_coeff(pt_rbf_sigma)
+    if pl_rbf_sigma is not None:
+        p.pl_weight_kind, p.pl_weight_coeff = 1, rbf_coeff(pl_rbf_sigma)
     return p
 
 
@@ -443,6 +457,14 @@ class Icp:
         _check(lib().cb_icp_correspondences(self.h, _p(i1), _p(i2), _p(v), C.byref(cnt)))
         c = cnt.value
         return i1[:c].astype(np.int64), i2[:c].astype(np.int64), v[:c]
+
+    def loop_cache(self):
+        """cb_icp_loop_cache: (T_search 3x4, nearest dst index per source point or -1, queries searched by the last iteration)."""
+        T = np.empty((3, 4), np.float32)
+        near = np.empty(self.src.n, np.int64)
+        cnt = C.c_uint64()
+        _check(lib().cb_icp_loop_cache(self.h, _p(T), _p(near), C.byref(cnt)))
+        return T, near, int(cnt.value)
 
     def residuals(self, T, **kw):
         prm = kw.pop("params", None) or icp_params(**kw)

@@ -285,6 +285,9 @@ int cb_comm_ipc_attach(cb_context* ctx, const void* handles) {
   CB_CHECK(ctx && handles, CB_ERR_INVALID, "null argument");
   CB_CHECK(ctx->world >= 1 && ctx->world <= kMaxRanks, CB_ERR_INVALID, "call cb_context_init_comm first");
   CB_CUDA(cudaSetDevice(ctx->device));
+  // One attach per context: the exchange tables keep the flag values of earlier passes, so a second mapping (with
+  // the pass counter restarted) could be satisfied by stale flags. A new communicator needs a new context.
+  CB_CHECK(!ctx->ex_attached, CB_ERR_INVALID, "cb_comm_ipc_attach was already called on this context");
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int p = 0; p < ctx->world; ++p) {
     if (p == ctx->rank) {
@@ -310,6 +313,7 @@ int cb_comm_ipc_attach(cb_context* ctx, const void* handles) {
   ctx->h_sync[0] = 0;
   CB_TRY(upload_peer_tables(ctx));
   ctx->ex_ready = true;
+  ctx->ex_attached = true;
   return CB_OK;
 }
 
@@ -616,6 +620,10 @@ static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, 
   a->max_d2 = prm->max_d2;
   a->w_pt = prm->w_pt;
   a->w_pl = prm->w_pl;
+  a->wk_pt = prm->pt_weight_kind == CB_WEIGHT_RBF;
+  a->wk_pl = prm->pl_weight_kind == CB_WEIGHT_RBF;
+  a->wc_pt = prm->pt_weight_coeff;
+  a->wc_pl = prm->pl_weight_coeff;
   for (int r = 0; r < 3; r++) a->dm[r] = icp->dst_mean[r];
   float smt[3];
   apply_point(T, icp->src_mean, smt);  // this->transform_ * src_mean_  (:189/:196)
@@ -686,7 +694,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   const bool bail_no_normals = w_pl_on && !dst_has_normals;
   const int max_opt = std::max(prm->max_opt_iter, 0);
   for (int it = 0; it < std::max(max_opt, 1); ++it) {
-    CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1 && !engine, &a));
+    CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1 && !engine, &a));  // (stores d2 too: the RBF weights of inner passes read it)
     const bool search = (it == 0);
     if (engine) {
       CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeCombined, w_pt_on,
@@ -736,6 +744,7 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
     if (!host_loop && !prm->host_loop && !engine_mode(prm) && one_step && (ctx->world == 1 || exchange_available(ctx)))
       return icp_loop_estimate(icp, prm, res);
   }
+  icp->loop_last = false;
   const uint64_t launches0 = ctx->launches;
   const int max_iter = std::max(prm->max_iter, 0);
   // Optional CUDA-event instrumentation, ONE bracket (2 events) per iteration: timing 1 = whole
@@ -875,28 +884,20 @@ int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_s
     CB_TRY(launch_icp_pass(ctx, a, kModeKnn, true, false, false));
     icp->nn_stored = true;
   }
-  // nn_pos is indexed by sorted src position and holds sorted dst positions: translate on the host
-  std::vector<int> pos(ns);
-  std::vector<float> nd2(ns);
-  std::vector<float4> sp(ns);
-  CB_CUDA(cudaMemcpyAsync(pos.data(), icp->d_nn_pos, ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CB_CUDA(cudaMemcpyAsync(nd2.data(), icp->d_nn_d2, ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  CB_CUDA(cudaMemcpyAsync(sp.data(), icp->src->d_pts, ns * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
-  const size_t nd = icp->dst->n;
-  std::vector<float4> dp(nd);
-  if (nd) CB_CUDA(cudaMemcpyAsync(dp.data(), icp->dst->d_pts, nd * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  // nn_pos is indexed by sorted src position and holds sorted dst positions: translate to ORIGINAL indices on the
+  // device (one small kernel) and download n_src ints + floats; the compaction in source order stays on the host
+  DeviceScope sc(ctx);
+  int* d_first = nullptr;
+  float* d_val = nullptr;
+  CB_TRY(sc.alloc(&d_first, ns));
+  CB_TRY(sc.alloc(&d_val, ns));
+  CB_TRY(launch_translate_matches(ctx, icp->d_nn_pos, icp->d_nn_d2, icp->src->d_pts, icp->dst->d_pts, (uint32_t)ns, d_first,
+                                  d_val));
+  std::vector<int> first(ns);
+  std::vector<float> val(ns);
+  CB_CUDA(cudaMemcpyAsync(first.data(), d_first, ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CB_CUDA(cudaMemcpyAsync(val.data(), d_val, ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
-  // this path is a getter, not the hot loop: rebuild (dst idx, d2) per ORIGINAL src index
-  std::vector<int64_t> first(ns, -1);
-  std::vector<float> val(ns, 0.f);
-  for (size_t i = 0; i < ns; i++) {
-    if (pos[i] < 0) continue;
-    int oi, di;
-    std::memcpy(&oi, &sp[i].w, 4);
-    std::memcpy(&di, &dp[pos[i]].w, 4);
-    first[oi] = di;
-    val[oi] = nd2[i];
-  }
   size_t k = 0;
   for (size_t i = 0; i < ns; i++) {
     if (first[i] < 0) continue;
@@ -906,6 +907,28 @@ int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_s
     ++k;
   }
   *count = k;
+  return CB_OK;
+}
+
+int cb_icp_loop_cache(cb_icp* icp, float* T_search12, int64_t* nearest, uint64_t* searched_last) {
+  CB_CHECK(icp, CB_ERR_INVALID, "null argument");
+  CB_CHECK(icp->loop_last && icp->h_state, CB_ERR_INVALID, "the last cb_icp_estimate did not run on the device loop");
+  cb_context* ctx = icp->ctx;
+  CB_CUDA(cudaSetDevice(ctx->device));
+  const size_t ns = icp->src->n;
+  if (T_search12) std::memcpy(T_search12, icp->T_search, sizeof(icp->T_search));
+  if (searched_last) *searched_last = icp->searched_last;
+  if (nearest && ns) {
+    DeviceScope sc(ctx);
+    int* d_first = nullptr;
+    CB_TRY(sc.alloc(&d_first, ns));
+    CB_TRY(launch_translate_matches(ctx, icp->d_nn_pos, nullptr, icp->src->d_pts, icp->dst->d_pts, (uint32_t)ns, d_first,
+                                    nullptr));
+    std::vector<int> first(ns);
+    CB_CUDA(cudaMemcpyAsync(first.data(), d_first, ns * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ns; i++) nearest[i] = first[i] < 0 ? -1 : (int64_t)first[i] + (int64_t)icp->dst->index_offset;
+  }
   return CB_OK;
 }
 

@@ -123,6 +123,7 @@ struct cb_context {
   unsigned long long* h_sync = nullptr;   // mapped pinned: [0] = flag, [8..8+32) = values (as doubles)
   unsigned long long seq = 0;             // passes issued with the exchange enabled
   bool ex_ready = false;                  // tables valid for the current (rank, world)
+  bool ex_attached = false;               // cb_comm_ipc_attach has mapped the peers' tables (once per context)
   bool pass_armed = false;                // the last reduction pass carried the fused exchange
 };
 

@@ -13,13 +13,15 @@ __device__ __forceinline__ constexpr int ut(int r, int c) { return r * 6 - (r * 
 
 // dp = matched destination point, (qx,qy,qz) = T * source point. load_dst_normal() / load_src_normal()
 // are only invoked when the metric needs them (has_pl / have_src_normal).
-// Args: anything with the fields T, Tin (Rigid), dm, sm (float[3]), w_pt, w_pl — IcpArgs, or the loop kernel's
-// per-block context. kIdentityTin = true skips the (identity) inner Gauss-Newton transform of the first pass:
+// Args: anything with the fields T, Tin (Rigid), dm, sm (float[3]), w_pt, w_pl, wk_pt, wk_pl, wc_pt, wc_pl — IcpArgs,
+// or the loop kernel's per-block context. corr_d2 = the correspondence's value (squared distance found by the search of
+// this ICP iteration): input of the RBF correspondence weight evaluators (common_pair_evaluators.hpp:46-79). kIdentityTin = true skips the (identity) inner Gauss-Newton transform of the first pass:
 // (1*x + (0*y + 0*z)) + 0 == x bit for bit for finite x.
 template <int MODE, bool kIdentityTin = false, class Args, class LoadDstNormal, class LoadSrcNormal>
 __device__ __forceinline__ void accumulate_pair(double* acc, const Args& a, bool has_pt, bool has_pl,
                                                 const float4 dp, float qx, float qy, float qz, bool have_src_normal,
-                                                LoadDstNormal load_dst_normal, LoadSrcNormal load_src_normal) {
+                                                LoadDstNormal load_dst_normal, LoadSrcNormal load_src_normal,
+                                                float corr_d2 = 0.f) {
   if constexpr (MODE == kModeP2P) {
     const double dx = dp.x, dy = dp.y, dz = dp.z, x = qx, y = qy, z = qz;
     acc[0] += 1.0;
@@ -58,7 +60,8 @@ __device__ __forceinline__ void accumulate_pair(double* acc, const Args& a, bool
     if (has_pt) {
       // eq_vecs E = [ [v]x ; I ] (6x3, :306-316)  ->  E E^T = [ |v|^2 I - v v^T , [v]x ; -[v]x , I ],
       // E e = [ v x e ; e ]
-      const double w = a.w_pt;
+      // weight = point_to_point_weight * point_corr_evaluator(i, j, value), in float      transform_estimation.hpp:302-304
+      const double w = a.wk_pt ? (double)__fmul_rn(a.w_pt, expf(__fmul_rn(a.wc_pt, corr_d2))) : (double)a.w_pt;
       const double V0 = v0, V1 = v1, V2 = v2, E0 = e0, E1 = e1, E2 = e2;
       A[ut(0, 0)] += w * (V1 * V1 + V2 * V2);
       A[ut(0, 1)] -= w * (V0 * V1);
@@ -106,7 +109,7 @@ __device__ __forceinline__ void accumulate_pair(double* acc, const Args& a, bool
       const float c2 = __fsub_rn(__fmul_rn(v0, n1), __fmul_rn(v1, n0));
       const double av[6] = {c0, c1, c2, n0, n1, n2};
       const double rd = (double)n0 * e0 + ((double)n1 * e1 + (double)n2 * e2);
-      const double w = a.w_pl;
+      const double w = a.wk_pl ? (double)__fmul_rn(a.w_pl, expf(__fmul_rn(a.wc_pl, corr_d2))) : (double)a.w_pl;  // :331-333
 #pragma unroll
       for (int r = 0; r < 6; r++) {
         const double wr = w * av[r];

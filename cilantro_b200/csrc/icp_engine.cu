@@ -190,7 +190,8 @@ Rigid rigid_of(const float* T12) { return rigid_from_t12(T12); }
 // ---- accumulation over the list ---------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kReduceBlock) pairs_pass_kernel(const IcpArgs a, const uint32_t* __restrict__ first,
-                                                                  const uint32_t* __restrict__ second, uint32_t m,
+                                                                  const uint32_t* __restrict__ second,
+                                                                  const float* __restrict__ pair_d2, uint32_t m,
                                                                   const float* __restrict__ dst_raw,
                                                                   const float* __restrict__ dst_nrm,
                                                                   const float* __restrict__ src_raw,
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kReduceBlock) pairs_pass_kernel(const IcpArgs 
     accumulate_pair<MODE>(
         acc, a, has_pt, has_pl, dp, qx, qy, qz, src_nrm != nullptr,
         [&] { return make_float4(dst_nrm[3 * i], dst_nrm[3 * i + 1], dst_nrm[3 * i + 2], 0.f); },
-        [&] { return make_float4(src_nrm[3 * j], src_nrm[3 * j + 1], src_nrm[3 * j + 2], 0.f); });
+        [&] { return make_float4(src_nrm[3 * j], src_nrm[3 * j + 1], src_nrm[3 * j + 2], 0.f); }, pair_d2[p]);
   }
   grid_reduce<NV>(acc, a.rs);
 }
@@ -224,12 +225,13 @@ int launch_pairs_pass(cb_context* ctx, const IcpArgs& a, const EnginePairs& pair
   ctx->pass_armed = false;
   const float* src_nrm = (mode == kModeCombined) ? src->d_raw_nrm : nullptr;
   if (mode == kModeP2P)
-    pairs_pass_kernel<kModeP2P><<<blocks, kReduceBlock, 0, ctx->stream>>>(args, pairs.first, pairs.second, pairs.count,
-                                                                        dst->d_raw, dst->d_raw_nrm, src->d_raw, src_nrm,
+    pairs_pass_kernel<kModeP2P><<<blocks, kReduceBlock, 0, ctx->stream>>>(args, pairs.first, pairs.second, pairs.d2,
+                                                                        pairs.count, dst->d_raw, dst->d_raw_nrm, src->d_raw, src_nrm,
                                                                         false, false);
   else
     pairs_pass_kernel<kModeCombined><<<blocks, kReduceBlock, 0, ctx->stream>>>(
-        args, pairs.first, pairs.second, pairs.count, dst->d_raw, dst->d_raw_nrm, src->d_raw, src_nrm, has_pt, has_pl);
+        args, pairs.first, pairs.second, pairs.d2, pairs.count, dst->d_raw, dst->d_raw_nrm, src->d_raw, src_nrm, has_pt,
+        has_pl);
   ctx->launches += 1;
   CB_CUDA(cudaGetLastError());
   return CB_OK;

@@ -79,12 +79,14 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
   float qx, qy, qz;
   apply_rigid(a.T, s.x, s.y, s.z, qx, qy, qz);
   int pos = -1;
+  float cd2 = 0.f;  // the correspondence's value (squared distance): input of the RBF weight evaluators
   if (SEARCH) {
     // every lane of the warp takes part in the pooled search (inactive tail lanes contribute no work)
     const int warm = (a.warm_pos && active) ? a.warm_pos[i] : -1;
     const Best best = warp_grid_nearest(a.dst, wsm[threadIdx.x >> 5], active, qx, qy, qz, a.max_d2, warm);
     if (active) {
       pos = (best.idx >= 0 && best.d2 < a.max_d2) ? best.pos : -1;
+      cd2 = best.d2;
       if (a.nn_pos) a.nn_pos[i] = pos;
       if (a.nn_d2) a.nn_d2[i] = best.d2;
       if (MODE == kModeKnn) {
@@ -95,13 +97,14 @@ __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(con
     }
   } else if (active) {
     pos = a.nn_pos[i];
+    if (MODE == kModeCombined && (a.wk_pt | a.wk_pl) && a.nn_d2) cd2 = a.nn_d2[i];
   }
   if constexpr (MODE != kModeKnn) {
     if (pos >= 0) {
       const float4 dp = __ldg(a.dst.pts + pos);
       accumulate_pair<MODE>(
           acc, a, has_pt, has_pl, dp, qx, qy, qz, a.src_nrm != nullptr, [&] { return __ldg(a.dst.nrm + pos); },
-          [&] { return __ldg(a.src_nrm + i); });
+          [&] { return __ldg(a.src_nrm + i); }, cd2);
     }
   }
   if constexpr (MODE != kModeKnn) grid_reduce_async<NV>(acc, a.rs, rsm);
@@ -152,7 +155,28 @@ __global__ void transform_points_kernel(const Rigid T, const float* __restrict__
   }
 }
 
+__global__ void translate_matches_kernel(const int* __restrict__ nn_pos, const float* __restrict__ nn_d2,
+                                         const float4* __restrict__ src_pts, const float4* __restrict__ dst_pts,
+                                         uint32_t n_src, int* __restrict__ out_first, float* __restrict__ out_val) {
+  for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_src; p += gridDim.x * blockDim.x) {
+    const int oi = __float_as_int(__ldg(&src_pts[p].w));
+    const int pos = nn_pos[p];
+    out_first[oi] = pos >= 0 ? __float_as_int(__ldg(&dst_pts[pos].w)) : -1;
+    if (out_val) out_val[oi] = nn_d2 ? nn_d2[p] : 0.f;
+  }
+}
+
 }  // namespace
+
+int launch_translate_matches(cb_context* ctx, const int* nn_pos, const float* nn_d2, const float4* src_pts,
+                             const float4* dst_pts, uint32_t n_src, int* out_first, float* out_val) {
+  if (n_src == 0) return CB_OK;
+  const int blocks = (int)std::max<uint32_t>(1, std::min<uint32_t>((uint32_t)ctx->sm_count * 8, (n_src + 255) / 256));
+  translate_matches_kernel<<<blocks, 256, 0, ctx->stream>>>(nn_pos, nn_d2, src_pts, dst_pts, n_src, out_first, out_val);
+  ctx->launches += 1;
+  CB_CUDA(cudaGetLastError());
+  return CB_OK;
+}
 
 int icp_grid_blocks(const cb_context* ctx) {
   // persistent-style launch: a whole number of waves of resident CTAs

@@ -26,6 +26,8 @@ struct IcpArgs {
   float max_d2;
   uint32_t prefetch_blocks;  // L2 prefetch look-ahead of the search kernel, in blocks (set by the launcher)
   float w_pt, w_pl;
+  int wk_pt, wk_pl;     // cb_weight_kind of the two correspondence weight evaluators
+  float wc_pt, wc_pl;   // RBF coefficients -0.5 / sigma^2
   float dm[3];   // dst_mean_
   float sm[3];   // transform_ * src_mean_
   // per-query results, indexed by position in the SORTED query cloud (nullable)
@@ -55,5 +57,10 @@ int launch_residuals(cb_context* ctx, const GridView& dst, const float4* src_pts
 int launch_transform_points(cb_context* ctx, const Rigid& T, const float* d_in, size_t n, float* d_out);
 
 int icp_grid_blocks(const cb_context* ctx);
+
+// Per sorted source position p: out_first[orig(p)] = original index of dst point nn_pos[p] (or -1),
+// out_val[orig(p)] = nn_d2[p] (nullable) - the getters' translation from sorted positions to caller indices.
+int launch_translate_matches(cb_context* ctx, const int* nn_pos, const float* nn_d2, const float4* src_pts,
+                             const float4* dst_pts, uint32_t n_src, int* out_first, float* out_val);
 
 }  // namespace cb

@@ -28,6 +28,7 @@
 #include "icp_object.hpp"
 #include "reduce.cuh"
 #include "solve_core.hpp"
+#include "solve_warp.cuh"
 #include "warp_search_wide.cuh"
 #include <algorithm>
 #include <cmath>
@@ -40,7 +41,7 @@ namespace {
 
 constexpr int kBlock = kReduceBlock;
 #ifndef CB_LOOP_QPT
-#define CB_LOOP_QPT 4
+#define CB_LOOP_QPT 16
 #endif
 constexpr int kQptWarm = CB_LOOP_QPT;  // 256-query chunks per block of the search kernel once the cache is warm
 constexpr float kUp18 = 1.0000038146972656f;    // 1 + 2^-18
@@ -53,6 +54,8 @@ struct LoopArgs {
   const float4* src_nrm;  // same order, or nullptr (symmetric metric when set)
   uint32_t n_src;
   float max_d2, w_pt, w_pl, tol;
+  int wk_pt, wk_pl;    // cb_weight_kind of the correspondence weight evaluators (combined metric)
+  float wc_pt, wc_pl;  // RBF coefficients
   float dm[3];        // dst_mean_
   float src_mean[3];  // src_mean_ (the kernel applies the current transform)
   int has_pt, has_pl;  // combined metric: which terms are on
@@ -71,6 +74,8 @@ struct BlockCtx {
   Rigid T, Tp;
   float dm[3], sm[3];
   float w_pt, w_pl;
+  int wk_pt, wk_pl;
+  float wc_pt, wc_pl;
   int have_prev, done;
 };
 
@@ -114,7 +119,7 @@ __device__ __noinline__ void loop_solve(const LoopArgs* ap, const BlockCtx* cxp,
     } else {
       float I[12], dn = 0.f;
       sc::t34_identity(I);
-      sc::gauss_newton_update(s, I, Titer, &dn);
+      sc::gauss_newton_apply(s + kCombinedValues, I, Titer, &dn);  // d_theta solved by the whole warp (solve6_warp)
       sc::uncenter(Titer, cx.dm, cx.sm);
     }
   }
@@ -132,6 +137,8 @@ __device__ __noinline__ void loop_solve(const LoopArgs* ap, const BlockCtx* cxp,
   st->n_corr = s[0];
   st->have_prev = 1;
   st->xseq = seq;
+  st->searched_last = st->searched_cur;
+  st->searched_cur = 0ull;
   if (delta < a.tol) st->done = 1;  // icp_base.hpp:83
   if (a.trace) st->trace[(st->iters - 1) & 63][3] = global_timer_ns();
   __threadfence();
@@ -143,6 +150,7 @@ struct ChunkPair {
   uint32_t i;
   int pos;
   float qx, qy, qz;
+  float d2;  // the match's squared distance (correspondence value)
 };
 
 template <bool kCold>
@@ -156,6 +164,7 @@ __device__ __forceinline__ ChunkPair search_chunk_body(const LoopArgs& a, const 
   cp.i = base + slot;
   cp.pos = -1;
   cp.qx = cp.qy = cp.qz = 0.f;
+  cp.d2 = 0.f;
   float slack = a.slack_first;
   int sd = -1;
   if (act) {
@@ -174,6 +183,7 @@ __device__ __forceinline__ ChunkPair search_chunk_body(const LoopArgs& a, const 
   const WideBest wb = warp_grid_nearest_wide(a.dst, *wsm, act, cp.qx, cp.qy, cp.qz, a.max_d2, sd, slack);
   if (act) {
     cp.pos = (wb.idx >= 0 && wb.d2 < a.max_d2) ? wb.pos : -1;
+    cp.d2 = wb.d2;
     a.cache_pos[cp.i] = cp.pos;
     a.cache_r[cp.i] = (wb.D2 > 0.f) ? __fmul_rd(__fsqrt_rd(wb.D2), kDown18) : 0.f;
   }
@@ -202,9 +212,19 @@ __device__ __forceinline__ void load_block_ctx(const LoopArgs& a, BlockCtx& cx) 
   cx.dm[0] = a.dm[0]; cx.dm[1] = a.dm[1]; cx.dm[2] = a.dm[2];
   cx.w_pt = a.w_pt;
   cx.w_pl = a.w_pl;
+  cx.wk_pt = a.wk_pt;
+  cx.wk_pl = a.wk_pl;
+  cx.wc_pt = a.wc_pt;
+  cx.wc_pl = a.wc_pl;
 }
 
-constexpr int kWarmQpt = 4;                     // queries per thread and tile of the cached pass
+#ifndef CB_WARM_QPT
+#define CB_WARM_QPT 4
+#endif
+#ifndef CB_WARM_MIN_BLOCKS
+#define CB_WARM_MIN_BLOCKS 2
+#endif
+constexpr int kWarmQpt = CB_WARM_QPT;           // queries per thread and tile of the cached pass
 constexpr int kWarmTile = kWarmQpt * kBlock;    // queries per tile of the cached pass
 
 // ---- kernel 1 of a warm iteration: the cached pass ------------------------------------------------------------------
@@ -217,7 +237,7 @@ constexpr int kWarmTile = kWarmQpt * kBlock;    // queries per tile of the cache
 // evaluated, and the moments are reduced ONCE per block (a per-tile reduction cost as much as the tile itself).
 // The block rows go through the same deterministic grid reduction into rs.result + 32.
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(kBlock, CB_WARM_MIN_BLOCKS) icp_cached_kernel(const __grid_constant__ LoopArgs a) {
   constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
   __shared__ BlockCtx cx;
   __shared__ AsyncReduceSmem<NV> rsm;
@@ -255,15 +275,20 @@ __global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_cons
 #pragma unroll 1
   for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const uint32_t base = tile * kWarmTile;
-    float4 p[kWarmQpt], sc[kWarmQpt];
+    float4 p[kWarmQpt], pn[kWarmQpt], sc[kWarmQpt];
     float rc[kWarmQpt];
     int sd[kWarmQpt];
+    const bool want_nrm = (MODE == kModeCombined) && a.has_pl != 0;
 #pragma unroll
     for (int k = 0; k < kWarmQpt; k++) {
       sc[k] = s[k];
       rc[k] = r[k];
       sd[k] = seed[k];
-      p[k] = (sd[k] >= 0 && rc[k] > 0.f) ? __ldg(a.dst.pts + sd[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool g = sd[k] >= 0 && rc[k] > 0.f;
+      p[k] = g ? __ldg(a.dst.pts + sd[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // the plane term's normal rides along with the match (inside accumulate_pair it would be a second dependent
+      // round trip per pair)
+      pn[k] = (g && want_nrm) ? __ldg(a.dst.nrm + sd[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     stream_loads(tile + gridDim.x);  // next tile of this block: in flight during the evaluation below
 #pragma unroll
@@ -283,9 +308,10 @@ __global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_cons
           // every reference point other than `seed` has a computed d2 above lim under the current transform
           const float lim = __fmul_rd(__fmul_rd(r2, r2), kDown17);
           bool pair = false;
+          float d2 = 0.f;
           if (sd[k] >= 0) {
             const float dx = __fsub_rn(qx, p[k].x), dy = __fsub_rn(qy, p[k].y), dz = __fsub_rn(qz, p[k].z);
-            float d2 = __fmul_rn(dx, dx);
+            d2 = __fmul_rn(dx, dx);
             d2 = __fadd_rn(d2, __fmul_rn(dy, dy));
             d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
             if (d2 < a.max_d2) {
@@ -301,10 +327,10 @@ __global__ void __launch_bounds__(kBlock, 2) icp_cached_kernel(const __grid_cons
           }
           if (!miss) a.cache_r[i] = r2;
           if (pair) {
-            const int pk = sd[k];
+            const float4 nk = pn[k];
             accumulate_pair<MODE, true>(
-                acc, cx, a.has_pt != 0, a.has_pl != 0, p[k], qx, qy, qz, a.src_nrm != nullptr,
-                [&] { return __ldg(a.dst.nrm + pk); }, [&] { return __ldg(a.src_nrm + i); });
+                acc, cx, a.has_pt != 0, a.has_pl != 0, p[k], qx, qy, qz, a.src_nrm != nullptr, [&] { return nk; },
+                [&] { return __ldg(a.src_nrm + i); }, d2);
           }
         }
       }
@@ -346,19 +372,23 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
     load_block_ctx(a, cx);
   }
   if (!kCold) {
-    static_assert(kCold || kWords <= 32, "one warp scans the tile's mask words");
-    if (warp == 1) {  // (warp 0's first lane is busy with the state)
-      const uint32_t w = (base >> 5) + lane;
-      const unsigned int m = (lane < kWords && w * 32u < a.n_src) ? __ldcg(a.miss_mask + w) : 0u;
-      unsigned int inc = __popc(m);
+    if (warp == 1) {  // (warp 0's first lane is busy with the state): mask words of the tile -> exclusive prefix of their populations
+      unsigned int carry = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if ((int)lane >= o) inc += t;
-      }
-      if (lane < kWords) {
-        smask[lane] = m;
-        spre[lane + 1] = inc;
+      for (int w0 = 0; w0 < kWords; w0 += 32) {
+        const uint32_t w = (base >> 5) + w0 + lane;
+        const unsigned int m = (w0 + (int)lane < kWords && w * 32u < a.n_src) ? __ldcg(a.miss_mask + w) : 0u;
+        unsigned int inc = __popc(m);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+          if ((int)lane >= o) inc += t;
+        }
+        if (w0 + (int)lane < kWords) {
+          smask[w0 + lane] = m;
+          spre[w0 + lane + 1] = carry + inc;
+        }
+        carry += __shfl_sync(0xffffffffu, inc, 31);
       }
       if (lane == 0) spre[0] = 0u;
     }
@@ -387,7 +417,10 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
       __syncthreads();
     }
   }
-  if (a.trace && tid == 0 && total > 0) atomicAdd(&a.st->trace[trace_slot][4], (unsigned long long)total);
+  if (tid == 0 && total > 0) {
+    atomicAdd(&a.st->searched_cur, (unsigned long long)total);
+    if (a.trace) atomicAdd(&a.st->trace[trace_slot][4], (unsigned long long)total);
+  }
   double tot = 0;
   if (total == 0) {
     // nothing to search in this tile (the usual case once the cache is warm): warp 0 contributes a zero row
@@ -404,7 +437,7 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
         const float4 dp = __ldg(a.dst.pts + cp.pos);
         accumulate_pair<MODE, true>(
             acc, cx, a.has_pt != 0, a.has_pl != 0, dp, cp.qx, cp.qy, cp.qz, a.src_nrm != nullptr,
-            [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); });
+            [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); }, cp.d2);
       }
     }
     if constexpr (kQpt > 1) {
@@ -417,7 +450,7 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
           const float4 dp = __ldg(a.dst.pts + cp.pos);
           accumulate_pair<MODE, true>(
               acc, cx, a.has_pt != 0, a.has_pl != 0, dp, cp.qx, cp.qy, cp.qz, a.src_nrm != nullptr,
-              [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); });
+              [&] { return __ldg(a.dst.nrm + cp.pos); }, [&] { return __ldg(a.src_nrm + cp.i); }, cp.d2);
         }
       }
     }
@@ -438,6 +471,15 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
   double* sbuf = rsm.slot[0];  // every warp of this block has arrived: the slots are free
   if (lane < NV) sbuf[lane] = tot;
   __syncwarp();
+  if constexpr (MODE == kModeCombined) {
+    // d_theta = AtA^-1 Atb with the augmented matrix spread over the warp; parked behind the totals (slot[1] is free too)
+    double x[6];
+    solve6_warp(sbuf, (int)lane, x);
+    if (lane == 0)
+#pragma unroll
+      for (int i = 0; i < 6; i++) sbuf[kCombinedValues + i] = x[i];
+    __syncwarp();
+  }
   if (lane == 0) loop_solve<MODE>(&a, &cx, sbuf, late ? 1 : 0, seq);
 }
 
@@ -467,6 +509,10 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
   a.max_d2 = prm->max_d2;
   a.w_pt = prm->w_pt;
   a.w_pl = prm->w_pl;
+  a.wk_pt = prm->pt_weight_kind == CB_WEIGHT_RBF;
+  a.wk_pl = prm->pl_weight_kind == CB_WEIGHT_RBF;
+  a.wc_pt = prm->pt_weight_coeff;
+  a.wc_pl = prm->pl_weight_coeff;
   a.tol = prm->tol;
   for (int r = 0; r < 3; r++) {
     a.dm[r] = icp->dst_mean[r];
@@ -496,7 +542,7 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
   const int blocks_cold = std::max(1, (int)((ns + kBlock - 1) / kBlock));
   const int blocks_search = std::max(1, (int)((ns + (size_t)kQptWarm * kBlock - 1) / ((size_t)kQptWarm * kBlock)));
   // persistent cached pass: a whole number of resident blocks per SM (never more blocks than tiles)
-  const int cached_per_sm = 2;  // __launch_bounds__ of icp_cached_kernel
+  const int cached_per_sm = CB_WARM_MIN_BLOCKS;  // __launch_bounds__ of icp_cached_kernel
   const int blocks_cached = std::max(1, std::min(ctx->sm_count * cached_per_sm, (int)((ns + kWarmTile - 1) / kWarmTile)));
   CB_TRY(get_reduce_scratch(ctx, blocks_cold, kMaxValues, &a.rs));
   if (!icp->d_miss_mask) CB_CUDA(cudaMalloc(&icp->d_miss_mask, (ns / 32 + 2) * sizeof(uint32_t)));
@@ -589,6 +635,8 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
   icp->nn_stored = false;  // d_nn_pos / d_nn_d2 hold the cache, not a per-query result list
   icp->warm_ok = false;
   icp->engine_last = false;
+  icp->loop_last = true;
+  icp->searched_last = hs->searched_last;
   std::memcpy(icp->T_search, hs->T_prev, sizeof(icp->T_search));
   icp->max_d2_search = prm->max_d2;
   std::memcpy(res->T, hs->T, sizeof(res->T));

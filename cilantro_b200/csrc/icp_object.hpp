@@ -21,6 +21,8 @@ struct LoopState {
   int pad_;
   unsigned long long xseq;  // fused-exchange pass number of the last executed iteration (Exchange::seq)
   double n_corr;      // correspondences of the last executed iteration (all ranks)
+  unsigned long long searched_cur;   // queries searched so far by the running iteration (this rank)
+  unsigned long long searched_last;  // ... by the last executed iteration
   double sums[32];    // its reduced moments / normal equations (all ranks)
   // CB_LOOP_TRACE=1: per executed iteration (mod 64): %globaltimer at kernel start / local reduction done /
   // peers' rows summed / state written, the number of queries that needed a search, %globaltimer at the start of
@@ -52,6 +54,8 @@ struct cb_icp {
   cb::LoopState* d_state = nullptr;
   cb::LoopState* h_state = nullptr;  // pinned
   uint32_t* d_miss_mask = nullptr;   // cached pass -> search kernel: one bit per sorted query
+  bool loop_last = false;            // the last estimate() ran on the device loop
+  uint64_t searched_last = 0;        // queries its last iteration searched again (CB_LOOP_TRACE / cb_icp_loop_cache)
 };
 
 namespace cb {

@@ -92,21 +92,41 @@ __device__ __forceinline__ void async_reduce_init(AsyncReduceSmem<NV>& sm) {
   __syncthreads();
 }
 
-// one warp sums rows r0..r1-1 of a [rows][NV] table (lane i owns value i; NV <= 32), 8 loads in flight
+// one warp sums rows r0..r1-1 of a [rows][NV] table; returns the total of value `lane` on lanes < NV.
+// NV <= 16: the two half-warps take the even / odd rows (16 loads in flight per lane pair instead of 8 — the fold
+// of a group of 64 block rows is a chain of dependent L2 round trips on the tail of every reduction kernel), the two
+// half sums are added even + odd. Fixed order in both cases.
 template <int NV>
 __device__ __forceinline__ double warp_sum_rows(const double* __restrict__ table, unsigned int r0, unsigned int r1,
                                                 int lane) {
   double s = 0;
-  if (lane < NV) {
-    unsigned int b = r0;
-    for (; b + 8 <= r1; b += 8) {
-      double t[8];
+  if constexpr (NV <= 16) {
+    const int v = lane & 15, par = lane >> 4;
+    if (v < NV) {
+      unsigned int b = r0 + par;
+      for (; b + 14 < r1; b += 16) {
+        double t[8];
 #pragma unroll
-      for (int u = 0; u < 8; u++) t[u] = __ldcg(table + (size_t)(b + u) * NV + lane);
+        for (int u = 0; u < 8; u++) t[u] = __ldcg(table + (size_t)(b + 2 * u) * NV + v);
 #pragma unroll
-      for (int u = 0; u < 8; u++) s += t[u];
+        for (int u = 0; u < 8; u++) s += t[u];
+      }
+      for (; b < r1; b += 2) s += __ldcg(table + (size_t)b * NV + v);
     }
-    for (; b < r1; ++b) s += __ldcg(table + (size_t)b * NV + lane);
+    const double other = __shfl_xor_sync(0xffffffffu, s, 16);
+    s = (par == 0) ? s + other : other + s;  // even rows + odd rows on both halves
+  } else {
+    if (lane < NV) {
+      unsigned int b = r0;
+      for (; b + 16 <= r1; b += 16) {
+        double t[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) t[u] = __ldcg(table + (size_t)(b + u) * NV + lane);
+#pragma unroll
+        for (int u = 0; u < 16; u++) s += t[u];
+      }
+      for (; b < r1; ++b) s += __ldcg(table + (size_t)b * NV + lane);
+    }
   }
   return s;
 }

@@ -301,8 +301,9 @@ CB_HD bool kabsch_from_moments(const double* s, const float* pd, const float* pq
 // One Gauss-Newton update (transform_estimation.hpp:346-357):
 //   d_theta = AtA^-1 Atb ; theta = atan(|w|) ; Ra = AngleAxis(theta, w/|w|) ; ta = cos(theta) v
 //   T_out = Ra * Translation(ta) * Ra * T_in
-CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout, float* dtheta_norm) {
-  double A[36], b[6], x[6];
+// d_theta = AtA^-1 Atb from the reduced normal equations s28 = {n, upper AtA (21), Atb (6)}
+CB_HD bool gauss_newton_solve(const double* s28, double* x) {
+  double A[36], b[6];
   int k = 1;
   for (int r = 0; r < 6; r++)
     for (int c = r; c < 6; c++) {
@@ -311,7 +312,11 @@ CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout,
       ++k;
     }
   for (int r = 0; r < 6; r++) b[r] = s28[22 + r];
-  const bool ok = la::solve6(A, b, x);
+  return la::solve6(A, b, x);
+}
+
+// the update from d_theta (already solved): T_out = Ra * Translation(ta) * Ra * T_in
+CB_HD void gauss_newton_apply(const double* x, const float* Tin, float* Tout, float* dtheta_norm) {
   float dth[6];
   for (int i = 0; i < 6; i++) dth[i] = (float)x[i];  // the reference holds d_theta in fp32
   const double na = sqrt((double)dth[0] * dth[0] + (double)dth[1] * dth[1] + (double)dth[2] * dth[2]);
@@ -350,6 +355,12 @@ CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout,
   double nn = 0;
   for (int i = 0; i < 6; i++) nn += (double)dth[i] * dth[i];
   if (dtheta_norm) *dtheta_norm = (float)sqrt(nn);
+}
+
+CB_HD bool gauss_newton_update(const double* s28, const float* Tin, float* Tout, float* dtheta_norm) {
+  double x[6];
+  const bool ok = gauss_newton_solve(s28, x);
+  gauss_newton_apply(x, Tin, Tout, dtheta_norm);
   return ok;
 }
 

@@ -43,6 +43,18 @@
 #include "../cilantro_b200.h"
 #include "b200_ply.hpp"
 
+// Eigen interoperability: where Eigen is installed, the stand-in containers below convert
+// from / to the Eigen types real cilantro code holds (VectorSet<float,3> = Eigen::Matrix<float,3,Dynamic>,
+// RigidTransform<float,3> = Eigen::Transform<float,3,Isometry>; core/data_containers.hpp:73-112,155-156,
+// core/space_transformations.hpp:54-55). Eigen3 is absent from the image this repo is built and tested in, so this
+// block is compiled only on a machine that has it (CILANTRO_B200_NO_EIGEN switches it off explicitly).
+#if !defined(CILANTRO_B200_NO_EIGEN) && defined(__has_include)
+#if __has_include(<Eigen/Dense>)
+#include <Eigen/Dense>
+#define CILANTRO_B200_HAS_EIGEN 1
+#endif
+#endif
+
 namespace cilantro {
 
 // ---- containers -----------------------------------------------------------------------------------
@@ -75,6 +87,13 @@ public:
     d_[3 * c + 1] = p[1];
     d_[3 * c + 2] = p[2];
   }
+#ifdef CILANTRO_B200_HAS_EIGEN
+  // same memory layout as Eigen::Matrix<float, 3, Dynamic> (column-major, packed xyz)
+  VectorSet3f(const Eigen::Matrix<float, 3, Eigen::Dynamic>& m) : d_(m.data(), m.data() + 3 * m.cols()) {}
+  Eigen::Map<Eigen::Matrix<float, 3, Eigen::Dynamic>> eigen() { return {d_.data(), 3, (Eigen::Index)cols()}; }
+  Eigen::Map<const Eigen::Matrix<float, 3, Eigen::Dynamic>> eigen() const { return {d_.data(), 3, (Eigen::Index)cols()}; }
+  operator Eigen::Matrix<float, 3, Eigen::Dynamic>() const { return eigen(); }
+#endif
 
 private:
   std::vector<float> d_;
@@ -89,6 +108,17 @@ public:
   ConstVectorSetMatrixMap3f(const std::vector<float>& s) : p_(s.data()), n_(s.size() / 3) {}
   ConstVectorSetMatrixMap3f(const std::vector<Vector3f>& s)
       : p_(s.empty() ? nullptr : s[0].data()), n_(s.size()) {}
+#ifdef CILANTRO_B200_HAS_EIGEN
+  // the sources ConstVectorSetMatrixMap<float,3> accepts in the reference (core/data_containers.hpp:73-112)
+  ConstVectorSetMatrixMap3f(const Eigen::Matrix<float, 3, Eigen::Dynamic>& m) : p_(m.data()), n_((size_t)m.cols()) {}
+  ConstVectorSetMatrixMap3f(const Eigen::Map<const Eigen::Matrix<float, 3, Eigen::Dynamic>>& m)
+      : p_(m.data()), n_((size_t)m.cols()) {}
+  ConstVectorSetMatrixMap3f(const Eigen::Map<Eigen::Matrix<float, 3, Eigen::Dynamic>>& m)
+      : p_(m.data()), n_((size_t)m.cols()) {}
+  ConstVectorSetMatrixMap3f(const std::vector<Eigen::Vector3f>& s)
+      : p_(s.empty() ? nullptr : s[0].data()), n_(s.size()) {}
+  Eigen::Map<const Eigen::Matrix<float, 3, Eigen::Dynamic>> eigen() const { return {p_, 3, (Eigen::Index)n_}; }
+#endif
   const float* data() const { return p_; }
   size_t cols() const { return n_; }
   size_t rows() const { return 3; }
@@ -141,6 +171,23 @@ public:
     }
     return r;
   }
+#ifdef CILANTRO_B200_HAS_EIGEN
+  // cilantro::RigidTransform<float,3> = Eigen::Transform<float,3,Eigen::Isometry> (core/space_transformations.hpp:54-55)
+  RigidTransform3f(const Eigen::Transform<float, 3, Eigen::Isometry>& T) {
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) m_[4 * r + c] = T.linear()(r, c);
+      m_[4 * r + 3] = T.translation()(r);
+    }
+  }
+  operator Eigen::Transform<float, 3, Eigen::Isometry>() const {
+    Eigen::Transform<float, 3, Eigen::Isometry> T = Eigen::Transform<float, 3, Eigen::Isometry>::Identity();
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) T.linear()(r, c) = m_[4 * r + c];
+      T.translation()(r) = m_[4 * r + 3];
+    }
+    return T;
+  }
+#endif
 
 private:
   float m_[12];
@@ -514,6 +561,9 @@ public:
 
   double getLastEstimateDeviceMilliseconds() const { return res_.gpu_ms_total; }
 
+protected:
+  cb_icp_params& params() { return prm_; }
+
 private:
   // both clouds in one call: the source upload overlaps the destination's grid build (cb_cloud_create_pair)
   void upload(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f* dst_n,
@@ -542,6 +592,84 @@ private:
 
 using SimplePointToPointMetricRigidICP3f = SimpleRigidICP3fB200<CB_ICP_POINT_TO_POINT>;
 using SimpleCombinedMetricRigidICP3f = SimpleRigidICP3fB200<CB_ICP_COMBINED>;
+
+// ---- correspondence weight evaluators (core/common_pair_evaluators.hpp) ---------------------------------------
+// The two evaluators a C ABI can carry, by kind + coefficient (cb_icp_params::pt_weight_kind ...). Same class names
+// and setters as the reference; operator() is kept so that host-side code calling the evaluator still compiles.
+template <typename ValueT = float, typename WeightT = ValueT>
+class UnityWeightEvaluator {  // :29-43
+public:
+  using InputScalar = ValueT;
+  using OutputScalar = WeightT;
+  constexpr WeightT operator()(ValueT) const { return (WeightT)1; }
+  constexpr WeightT operator()(size_t, size_t, ValueT) const { return (WeightT)1; }
+  static constexpr int b200_kind() { return CB_WEIGHT_UNITY; }
+  float b200_coeff() const { return 0.f; }
+};
+
+template <typename ValueT = float, typename WeightT = ValueT, bool distances_are_squared = true>
+class RBFKernelWeightEvaluator {  // :46-79
+  static_assert(distances_are_squared, "ICP correspondences carry squared distances: only the <.., true> evaluator maps to the device path");
+
+public:
+  using InputScalar = ValueT;
+  using OutputScalar = WeightT;
+  RBFKernelWeightEvaluator() : coeff_(-(WeightT)(0.5)) {}
+  RBFKernelWeightEvaluator(ValueT sigma) : coeff_(-(WeightT)(0.5) / (sigma * sigma)) {}
+  RBFKernelWeightEvaluator& setSigma(ValueT sigma) {
+    coeff_ = -(WeightT)(0.5) / (sigma * sigma);
+    return *this;
+  }
+  WeightT operator()(ValueT dist) const { return std::exp(coeff_ * static_cast<WeightT>(dist)); }
+  WeightT operator()(size_t, size_t, ValueT dist) const { return std::exp(coeff_ * static_cast<WeightT>(dist)); }
+  static constexpr int b200_kind() { return CB_WEIGHT_RBF; }
+  float b200_coeff() const { return (float)coeff_; }
+
+private:
+  WeightT coeff_;
+};
+
+// CombinedMetricRigidICP3f<CorrSearchT, PointToPointCorrWeightEvaluatorT, PointToPlaneCorrWeightEvaluatorT>
+// (registration/icp_common_instances.hpp:29-31 over icp_single_transform_combined_metric.hpp:9-101): the general form
+// with caller-owned evaluators, held by reference like the reference does (their sigma is read at every estimate()).
+// The correspondence search engine argument of the reference is this object's own engine
+// (correspondenceSearchEngine()); any evaluator type other than the two above is a compile-time error.
+template <class PointToPointCorrWeightEvaluatorT = UnityWeightEvaluator<float, float>,
+          class PointToPlaneCorrWeightEvaluatorT = UnityWeightEvaluator<float, float>>
+class CombinedMetricRigidICP3f : public SimpleRigidICP3fB200<CB_ICP_COMBINED> {
+  using Base = SimpleRigidICP3fB200<CB_ICP_COMBINED>;
+
+public:
+  using PointToPointCorrespondenceWeightEvaluator = PointToPointCorrWeightEvaluatorT;
+  using PointToPlaneCorrespondenceWeightEvaluator = PointToPlaneCorrWeightEvaluatorT;
+  CombinedMetricRigidICP3f(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
+                           const ConstVectorSetMatrixMap3f& src, PointToPointCorrWeightEvaluatorT& point_corr_eval,
+                           PointToPlaneCorrWeightEvaluatorT& plane_corr_eval)
+      : Base(dst, dst_n, src), pt_(point_corr_eval), pl_(plane_corr_eval) {}
+  CombinedMetricRigidICP3f(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& dst_n,
+                           const ConstVectorSetMatrixMap3f& src, const ConstVectorSetMatrixMap3f& src_n,
+                           PointToPointCorrWeightEvaluatorT& point_corr_eval, PointToPlaneCorrWeightEvaluatorT& plane_corr_eval)
+      : Base(dst, dst_n, src, src_n), pt_(point_corr_eval), pl_(plane_corr_eval) {}
+  PointToPointCorrWeightEvaluatorT& pointToPointCorrespondenceWeightEvaluator() { return pt_; }
+  PointToPlaneCorrWeightEvaluatorT& pointToPlaneCorrespondenceWeightEvaluator() { return pl_; }
+  CombinedMetricRigidICP3f& estimate() {
+    this->params().pt_weight_kind = PointToPointCorrWeightEvaluatorT::b200_kind();
+    this->params().pl_weight_kind = PointToPlaneCorrWeightEvaluatorT::b200_kind();
+    this->params().pt_weight_coeff = pt_.b200_coeff();
+    this->params().pl_weight_coeff = pl_.b200_coeff();
+    Base::estimate();
+    return *this;
+  }
+  CombinedMetricRigidICP3f& estimate(size_t max_iter, float conv_tol) {
+    this->setMaxNumberOfIterations(max_iter);
+    this->setConvergenceTolerance(conv_tol);
+    return estimate();
+  }
+
+private:
+  PointToPointCorrWeightEvaluatorT& pt_;
+  PointToPlaneCorrWeightEvaluatorT& pl_;
+};
 
 // transformPoints(tform, in, out) — core/space_transformations.hpp:203-216
 inline void transformPoints(const RigidTransform3f& tform, const ConstVectorSetMatrixMap3f& points, VectorSet3f& result) {
@@ -626,6 +754,16 @@ public:
     defaults();
   }
 
+  // (dst, src, dst_ind, src_ind): pair k = (dst point dst_ind[k], src point src_ind[k])
+  // (model_estimation/ransac_transform_estimator.hpp:46-59)
+  template <typename IdxT>
+  RigidTransformRANSACEstimator3f(const ConstVectorSetMatrixMap3f& dst, const ConstVectorSetMatrixMap3f& src,
+                                  const std::vector<IdxT>& dst_ind, const std::vector<IdxT>& src_ind)
+      : n_(dst_ind.size()), dst_g_(gather_ind(dst, dst_ind, dst_ind.size())), src_g_(gather_ind(src, src_ind, dst_ind.size())),
+        dst_(dst_g_), src_(src_g_) {
+    defaults();
+  }
+
   // RandomSampleConsensusBase setters (model_estimation/ransac_base.hpp:29-62)
   RigidTransformRANSACEstimator3f& setMaxInlierResidual(float t) { thresh_ = t; return *this; }
   RigidTransformRANSACEstimator3f& setTargetInlierCount(size_t c) { target_ = c; return *this; }
@@ -676,6 +814,12 @@ private:
     for (size_t i = 0; i < corr.size(); i++) out.setCol(i, pts.col(first ? corr[i].indexInFirst : corr[i].indexInSecond));
     return out;
   }
+  template <typename IdxT>
+  static VectorSet3f gather_ind(const ConstVectorSetMatrixMap3f& pts, const std::vector<IdxT>& ind, size_t count) {
+    VectorSet3f out(3, count);  // :53-58 (the loop runs over dst_ind.size() for both sets)
+    for (size_t i = 0; i < count; i++) out.setCol(i, pts.col((size_t)ind[i]));
+    return out;
+  }
   size_t n_;
   VectorSet3f dst_g_, src_g_;
   b200::CloudHandle dst_, src_;
@@ -695,10 +839,54 @@ public:
     b200::CloudHandle c(data);
     b200::check(cb_pca(b200::Context::get(), c.h, mean_.data(), cov_.data(), evals_.data(), evecs_.data()), "cb_pca");
   }
+  // subset constructor (core/principal_component_analysis.hpp:24-30): the listed points only
+  template <typename ContainerT, typename = decltype(std::declval<const ContainerT&>().begin())>
+  PrincipalComponentAnalysis3f(const ConstVectorSetMatrixMap3f& data, const ContainerT& subset, bool /*parallel*/ = false) {
+    std::vector<float> sel;
+    for (auto it = subset.begin(); it != subset.end(); ++it) {
+      const Vector3f p = data.col((size_t)*it);
+      sel.insert(sel.end(), {p[0], p[1], p[2]});
+    }
+    b200::CloudHandle c(ConstVectorSetMatrixMap3f(sel.data(), sel.size() / 3));
+    b200::check(cb_pca(b200::Context::get(), c.h, mean_.data(), cov_.data(), evals_.data(), evecs_.data()), "cb_pca");
+  }
   const Vector3f& getDataMean() const { return mean_; }
   const std::array<float, 9>& getDataCovariance() const { return cov_; }  // row-major 3x3
   const Vector3f& getEigenValues() const { return evals_; }               // descending
   const std::array<float, 9>& getEigenVectors() const { return evecs_; }  // row-major, columns = eigenvectors
+
+  // project(points, target_dim) (:46-49): target_dim x N, column-major = eigenvectors.leftCols(target_dim)^T (p - mean).
+  // A 3 x k map applied once after the device pass, like the reference's Eigen expression (not part of the hot path).
+  std::vector<float> project(const ConstVectorSetMatrixMap3f& points, size_t target_dim) const {
+    const size_t k = std::min<size_t>(target_dim, 3), n = points.cols();
+    std::vector<float> out(k * n);
+    for (size_t i = 0; i < n; i++) {
+      const Vector3f p = points.col(i);
+      const float c[3] = {p[0] - mean_[0], p[1] - mean_[1], p[2] - mean_[2]};
+      for (size_t j = 0; j < k; j++) out[k * i + j] = evecs_[j] * c[0] + evecs_[3 + j] * c[1] + evecs_[6 + j] * c[2];
+    }
+    return out;
+  }
+  template <size_t DimOut>
+  std::vector<float> project(const ConstVectorSetMatrixMap3f& points) const {  // :51-57
+    static_assert(DimOut >= 1 && DimOut <= 3, "projection dimension of a 3-D PCA");
+    return project(points, DimOut);
+  }
+  // reconstruct(points) (:59-70): points is dim_in x N column-major; returns 3 x N = leftCols(dim_in) * points + mean
+  VectorSet3f reconstruct(const float* points, size_t dim_in, size_t n) const {
+    const size_t k = std::min<size_t>(dim_in, 3);
+    VectorSet3f out(3, n);
+    for (size_t i = 0; i < n; i++) {
+      float q[3] = {mean_[0], mean_[1], mean_[2]};
+      for (size_t j = 0; j < k; j++)
+        for (int r = 0; r < 3; r++) q[r] += evecs_[3 * r + j] * points[dim_in * i + j];
+      out.setCol(i, Vector3f(q[0], q[1], q[2]));
+    }
+    return out;
+  }
+  VectorSet3f reconstruct(const std::vector<float>& points, size_t dim_in) const {
+    return reconstruct(points.data(), dim_in, dim_in ? points.size() / dim_in : 0);
+  }
 
 private:
   Vector3f mean_, evals_;

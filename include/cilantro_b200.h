@@ -211,7 +211,20 @@ typedef struct cb_icp_params {
   int32_t host_loop;           /* 0 (default): iterations run back to back on the device where the configuration allows it
                                   (default engine, one Gauss-Newton step per iteration); 1: host-driven loop (A/B, tests) */
   double inlier_fraction;      /* keep the llround(fraction * M) closest pairs when 0 < fraction < 1; default 1 */
+  /* Correspondence weight evaluators of the combined / symmetric metric (the PointToPointCorrWeightEvaluatorT /
+   * PointToPlaneCorrWeightEvaluatorT template arguments of CombinedMetricSingleTransformICP, consumed at
+   * registration/transform_estimation.hpp:302-304 and :331-333): weight = metric weight * evaluator(i, j, d2).
+   * Arbitrary functors cannot cross a C ABI; the two evaluators of core/common_pair_evaluators.hpp that make sense
+   * here are selected by kind: CB_WEIGHT_UNITY (UnityWeightEvaluator, :29-43, the default) and CB_WEIGHT_RBF
+   * (RBFKernelWeightEvaluator<float, float, true>, :46-79: exp(coeff * d2) with coeff = -0.5f / (sigma * sigma),
+   * d2 = the correspondence's squared distance). */
+  int32_t pt_weight_kind;
+  int32_t pl_weight_kind;
+  float pt_weight_coeff;
+  float pl_weight_coeff;
 } cb_icp_params;
+
+typedef enum cb_weight_kind { CB_WEIGHT_UNITY = 0, CB_WEIGHT_RBF = 1 } cb_weight_kind;
 
 typedef enum cb_search_dir {
   CB_SECOND_TO_FIRST = 0, /* queries = transformed src, tree = dst (the default) */
@@ -252,6 +265,13 @@ int cb_icp_residuals(cb_icp* icp, const cb_icp_params* prm, const float* T12, fl
  * combined: sums[28] = {n, AtA upper triangle row-major (21), Atb (6)}. Used by the parity tests
  * and by callers that do their own reduction. */
 int cb_icp_accumulate(cb_icp* icp, const cb_icp_params* prm, const float* T12, double* sums, int cap);
+
+/* Inspection of the device-resident loop's per-query cache after cb_icp_estimate took that path (parity tests):
+ * T_search12 = the transform the LAST executed iteration searched with; nearest[i] = original index of the
+ * destination point the loop holds as source point i's nearest neighbour under that transform (whether or not it
+ * is inside the radius), -1 = none known; searched_last = queries the last iteration had to search again.
+ * Returns CB_ERR_INVALID when the last estimate() did not run on the device loop. */
+int cb_icp_loop_cache(cb_icp* icp, float* T_search12, int64_t* nearest, uint64_t* searched_last);
 
 /* Host-only O(1) solves (no device needed; exported so the N>1 logic is testable on CPU). */
 /* estimateTransformPointToPointMetric from moments — transform_estimation.hpp:25-47. Returns 1 if n>=3. */

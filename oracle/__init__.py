@@ -55,6 +55,10 @@ class IcpParams(C.Structure):
         ("reserved_", C.c_int32),
         ("inlier_fraction", C.c_double),
         ("f2s_fn", C.c_void_p),
+        ("pt_weight_kind", C.c_int32),
+        ("pl_weight_kind", C.c_int32),
+        ("pt_weight_coeff", C.c_float),
+        ("pl_weight_coeff", C.c_float),
     ]
 
 
@@ -304,8 +308,10 @@ def estimate_combined(dst_p, dst_n, src_p, idx_first, idx_second, w_pt, w_pl, ma
 def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, tol=1e-5, max_d2=1e-4,
         w_pt=0.0, w_pl=1.0, max_opt_iter=1, opt_tol=1e-5, T_init=None, accum_double=False, parallel=False,
         log=False, search_dir="second_to_first", inlier_fraction=1.0, require_reciprocal=False, one_to_one=False,
-        f2s_reference=False):
-    """icp_base.hpp:68-87 driving the p2p or combined/symmetric estimator. Returns a dict."""
+        f2s_reference=False, pt_rbf_sigma=None, pl_rbf_sigma=None):
+    """icp_base.hpp:68-87 driving the p2p or combined/symmetric estimator. Returns a dict.
+    pt_rbf_sigma / pl_rbf_sigma: RBFKernelWeightEvaluator<float, float, true>(sigma) as the point-to-point /
+    point-to-plane correspondence weight evaluator (common_pair_evaluators.hpp:46-79); None = UnityWeightEvaluator."""
     dst_p, src_p = _f32(dst_p), _f32(src_p)
     dst_n = _f32(dst_n) if dst_n is not None else None
     src_n = _f32(src_n) if src_n is not None else None
@@ -320,6 +326,11 @@ def icp(dst_p, src_p, knn, metric="p2p", dst_n=None, src_n=None, max_iter=15, to
     prm.opt_tol = opt_tol
     prm.accum_double = int(accum_double)
     prm.parallel = int(parallel)
+    for kind, coeff, sigma in (("pt_weight_kind", "pt_weight_coeff", pt_rbf_sigma), ("pl_weight_kind", "pl_weight_coeff", pl_rbf_sigma)):
+        if sigma is not None:
+            sg = np.float32(sigma)
+            setattr(prm, kind, 1)
+            setattr(prm, coeff, float(np.float32(-0.5) / (sg * sg)))  # coeff_ = -(WeightT)(0.5) / (sigma * sigma), in float
     Ti = identity() if T_init is None else _T(T_init)
     for i, v in enumerate(Ti.reshape(-1)):
         prm.T_init[i] = float(v)

@@ -303,16 +303,26 @@ static bool kabsch_corr(const float* dst, const float* src, const std::vector<Co
 // ---------------------------------------------------------------------------------------------
 // estimateTransformCombinedMetric rigid 3-D — transform_estimation.hpp:238-367, and
 // estimateTransformSymmetricMetric — :608-739 (src_n != nullptr; n = n_dst + R_tform n_src).
-// UnityWeightEvaluator (common_pair_evaluators.hpp:29-43) => weight = metric weight.
+// Correspondence weight evaluators: UnityWeightEvaluator (common_pair_evaluators.hpp:29-43) => weight = metric
+// weight; RBFKernelWeightEvaluator<float, float, true> (:46-79) => metric weight * std::exp(coeff_ * value) with
+// coeff_ = -(0.5f) / (sigma * sigma), value = the correspondence's squared distance (called as
+// evaluator(indexInFirst, indexInSecond, value), transform_estimation.hpp:302-304 / :331-333).
 // ---------------------------------------------------------------------------------------------
+struct CorrWeights {
+  int pt_kind = 0, pl_kind = 0;  // 0 unity, 1 RBF
+  float pt_coeff = -0.5f, pl_coeff = -0.5f;
+};
+static inline float corr_weight(int kind, float coeff, float value) { return kind ? std::exp(coeff * value) : 1.f; }
+
 template <typename Acc>
 static void accumulate_combined(const float* dst_p, const float* dst_n, const float* src_p, const float* src_n,
                                 const Corr* corr, size_t begin, size_t end, bool has_pt, bool has_pl,
-                                float w_pt, float w_pl, const T34& tform, const float* dst_mean,
-                                const float* src_mean, Acc AtA[36], Acc Atb[6]) {
+                                float w_pt_metric, float w_pl_metric, const T34& tform, const float* dst_mean,
+                                const float* src_mean, Acc AtA[36], Acc Atb[6], const CorrWeights& cw = CorrWeights()) {
   if (has_pt) {  // :292-321
     for (size_t i = begin; i < end; i++) {
       const Corr& c = corr[i];
+      const float w_pt = w_pt_metric * corr_weight(cw.pt_kind, cw.pt_coeff, c.value);  // :302-304
       float d[3], sm[3], s[3];
       for (int r = 0; r < 3; r++) d[r] = dst_p[3 * c.indexInFirst + r] - dst_mean[r];
       for (int r = 0; r < 3; r++) sm[r] = src_p[3 * c.indexInSecond + r] - src_mean[r];
@@ -340,6 +350,7 @@ static void accumulate_combined(const float* dst_p, const float* dst_n, const fl
   if (has_pl) {  // :323-343 / :694-715
     for (size_t i = begin; i < end; i++) {
       const Corr& c = corr[i];
+      const float w_pl = w_pl_metric * corr_weight(cw.pl_kind, cw.pl_coeff, c.value);  // :331-333
       float d[3], n[3], sm[3], s[3];
       for (int r = 0; r < 3; r++) d[r] = dst_p[3 * c.indexInFirst + r] - dst_mean[r];
       for (int r = 0; r < 3; r++) n[r] = dst_n[3 * c.indexInFirst + r];
@@ -370,7 +381,7 @@ template <typename Acc>
 static bool estimate_combined(const float* dst_p, const float* dst_n, size_t n_dst_p, size_t n_dst_n,
                               const float* src_p, const float* src_n, const std::vector<Corr>& corr,
                               float w_pt, float w_pl, size_t max_iter, float tol, const float* dst_mean,
-                              const float* src_mean, bool parallel, T34& tform) {
+                              const float* src_mean, bool parallel, T34& tform, const CorrWeights& cw = CorrWeights()) {
   tform = t34_identity();  // :262
   const bool has_pt = !corr.empty() && (w_pt > 0.f);
   const bool has_pl = !corr.empty() && (w_pl > 0.f);
@@ -382,7 +393,7 @@ static bool estimate_combined(const float* dst_p, const float* dst_n, size_t n_d
     for (int i = 0; i < 6; i++) Atb[i] = 0;
     if (!parallel) {
       accumulate_combined<Acc>(dst_p, dst_n, src_p, src_n, corr.data(), 0, corr.size(), has_pt, has_pl, w_pt,
-                               w_pl, tform, dst_mean, src_mean, AtA, Atb);
+                               w_pl, tform, dst_mean, src_mean, AtA, Atb, cw);
     } else {
       // ENABLE_NON_DETERMINISTIC_PARALLELISM=ON build (:285-290): per-thread partials, summed.
 #ifdef _OPENMP
@@ -401,7 +412,7 @@ static bool estimate_combined(const float* dst_p, const float* dst_n, size_t n_d
         size_t chunk = (corr.size() + nt - 1) / nt;
         size_t b = std::min(corr.size(), chunk * t), e = std::min(corr.size(), b + chunk);
         accumulate_combined<Acc>(dst_p, dst_n, src_p, src_n, corr.data(), b, e, has_pt, has_pl, w_pt, w_pl,
-                                 tform, dst_mean, src_mean, &part[(size_t)t * 42], &part[(size_t)t * 42 + 36]);
+                                 tform, dst_mean, src_mean, &part[(size_t)t * 42], &part[(size_t)t * 42 + 36], cw);
       }
       for (int t = 0; t < nt; t++) {
         for (int i = 0; i < 36; i++) AtA[i] += part[(size_t)t * 42 + i];
@@ -517,6 +528,9 @@ struct orc_icp_params {
   // FIRST_TO_SECOND / BOTH: 1-NN of the dst points among the transformed src points, tree rebuilt per call.
   // nullptr = orc_knn1_brute; tests pass oracle/_ref's ref_knn1_build_query (the reference's own nanoflann).
   void (*f2s_fn)(const float* ref_pts, size_t nref, const float* qry, size_t nq, float max_d2, int64_t* idx, float* d2);
+  // correspondence weight evaluators of the combined metric: 0 = UnityWeightEvaluator, 1 = RBFKernelWeightEvaluator
+  int32_t pt_weight_kind, pl_weight_kind;
+  float pt_weight_coeff, pl_weight_coeff;  // -(0.5f) / (sigma * sigma)
 };
 
 // CorrespondenceSearchKDTree::findCorrespondences(tform) — correspondence_search_kd_tree.hpp:107-229:
@@ -650,14 +664,19 @@ ORC_API void orc_icp(const float* dst_p, const float* dst_n, size_t n_dst, const
         orc_rotate_vectors(T.m, src_n, n_src, src_n_trans.data());  // transformNormals :183
         sn = src_n_trans.data();
       }
+      CorrWeights cw;
+      cw.pt_kind = prm->pt_weight_kind;
+      cw.pl_kind = prm->pl_weight_kind;
+      cw.pt_coeff = prm->pt_weight_coeff;
+      cw.pl_coeff = prm->pl_weight_coeff;
       if (prm->accum_double)
         estimate_combined<double>(dst_p, dst_n, n_dst, n_dst, src_trans.data(), sn, corr, prm->w_pt, prm->w_pl,
                                   (size_t)prm->max_opt_iter, prm->opt_tol, dst_mean, src_mean_t,
-                                  prm->parallel != 0, Titer);
+                                  prm->parallel != 0, Titer, cw);
       else
         estimate_combined<float>(dst_p, dst_n, n_dst, n_dst, src_trans.data(), sn, corr, prm->w_pt, prm->w_pl,
                                  (size_t)prm->max_opt_iter, prm->opt_tol, dst_mean, src_mean_t,
-                                 prm->parallel != 0, Titer);
+                                 prm->parallel != 0, Titer, cw);
     }
     reorthonormalize(Titer);  // :207-211 / p2p :56-60
     T = compose(Titer, T);    // :213

@@ -75,6 +75,22 @@ int main() {
     CHECK(std::fabs(pca.getEigenValues()[0] - 8.f * 250000.f / 7.f) < 1.f);
     CHECK(std::fabs(pca.getEigenValues()[2] - 8.f * 0.25f / 7.f) < 1e-5f);
     CHECK(std::fabs(std::fabs(pca.getEigenVectors()[2 * 3 + 0]) - 1.f) < 1e-5f);  // first eigenvector = +-e_z
+    // project / reconstruct (core/principal_component_analysis.hpp:46-72): full-rank round trip, rank-1 keeps z only
+    std::vector<float> pr3 = pca.project(pts, 3);
+    cilantro::VectorSet3f back = pca.reconstruct(pr3, 3);
+    for (size_t i = 0; i < pts.size(); i++)
+      for (int r = 0; r < 3; r++) CHECK(std::fabs(back(r, i) - pts[i][r]) < 2e-3f);
+    std::vector<float> pr1 = pca.project<1>(pts);
+    CHECK(pr1.size() == pts.size());
+    cilantro::VectorSet3f back1 = pca.reconstruct(pr1, 1);
+    for (size_t i = 0; i < pts.size(); i++) {
+      CHECK(std::fabs(std::fabs(pr1[i]) - 500.f) < 1e-2f);
+      CHECK(std::fabs(back1(2, i) - pts[i][2]) < 1e-2f && std::fabs(back1(0, i) - 0.5f) < 1e-3f);
+    }
+    // subset constructor: the four points with z = 0 -> no variance along z
+    std::vector<size_t> subset = {0, 2, 4, 6};
+    cilantro::PrincipalComponentAnalysis3f pca_sub(pts, subset);
+    CHECK(std::fabs(pca_sub.getDataMean()[2]) < 1e-6f && std::fabs(pca_sub.getEigenValues()[2]) < 1e-3f);
   }
   // ---- rigid_icp.cpp recipe on a synthetic surface ------------------------------------------------------
   std::mt19937 rng(7);
@@ -172,6 +188,22 @@ int main() {
     auto residuals = icp.getResiduals();
     CHECK(residuals.size() == N);
     CHECK(icp.getCorrespondences().size() > N / 2);
+    // the general class with caller-owned correspondence weight evaluators (icp_single_transform_combined_metric.hpp:9-101):
+    // RBF weights on both terms; a very wide kernel must reproduce the unity-weight result, a narrow one still converges
+    cilantro::RBFKernelWeightEvaluator<float, float, true> w_pt_eval(1e3f), w_pl_eval(1e3f);
+    cilantro::CombinedMetricRigidICP3f<cilantro::RBFKernelWeightEvaluator<float, float, true>,
+                                       cilantro::RBFKernelWeightEvaluator<float, float, true>>
+        icp_w(dst.points, dst.normals, src.points, w_pt_eval, w_pl_eval);
+    icp_w.setMaxNumberOfOptimizationStepIterations(1).setPointToPointMetricWeight(0.0f).setPointToPlaneMetricWeight(1.0f);
+    icp_w.correspondenceSearchEngine().setMaxDistance(0.1f * 0.1f);
+    icp_w.setConvergenceTolerance(1e-4f).setMaxNumberOfIterations(30);
+    CHECK(frob(icp_w.estimate().getTransform(), tf_est) < 1e-5f);
+    icp_w.pointToPlaneCorrespondenceWeightEvaluator().setSigma(0.02f);
+    icp_w.estimate();
+    std::printf("combined ICP, RBF(0.02) plane weights: %zu iterations, |T - tf_ref^-1|_F = %.2e\n",
+                icp_w.getNumberOfPerformedIterations(), frob(icp_w.getTransform(), tf_ref.inverse()));
+    CHECK(icp_w.hasConverged() && frob(icp_w.getTransform(), tf_ref.inverse()) < 2e-2f);
+    CHECK(frob(icp_w.getTransform(), tf_est) > 0.f);  // the weights do change the estimate
   }
   {
     cilantro::SimplePointToPointMetricRigidICP3f icp(dst.points, src.points);
@@ -240,6 +272,13 @@ int main() {
     CHECK(te.getNumberOfInliers() > 200 && te.getNumberOfInliers() < 300);
     CHECK(frob(tf_est, tf_ref) < 5e-3f);
     CHECK(te.getModelResiduals().size() == M);
+    // (dst, src, dst_ind, src_ind) constructor (ransac_transform_estimator.hpp:46-59): the same pairs by index vectors
+    std::vector<size_t> di(M), si(M);
+    for (size_t i = 0; i < M; i++) di[i] = si[i] = i;
+    cilantro::RigidTransformRANSACEstimator3f<> te2(d, s, di, si);
+    te2.setMaxInlierResidual(0.01f).setTargetInlierCount((size_t)(0.50 * M)).setMaxNumberOfIterations(250).setReEstimationStep(true);
+    te2.setRandomSeed(99);
+    CHECK(frob(te2.estimate().getModel(), tf_est) == 0.f && te2.getNumberOfInliers() == te.getNumberOfInliers());
   }
   std::printf("all C++ shim checks passed\n");
   return 0;

@@ -33,6 +33,19 @@ def test_reference_examples_through_cpp_shims(cb, tmp_path):
     assert "all C++ shim checks passed" in out.stdout
 
 
+def test_eigen_adapters_type_check(tmp_path):
+    """The `#if __has_include(<Eigen/Dense>)` adapters (VectorSet / ConstVectorSetMatrixMap / RigidTransform <-> Eigen).
+    Eigen3 is absent from this image: they are compiled against tests/cpp/eigen_stub (a minimal stand-in with Eigen's
+    layout and accessor names), or against the real Eigen where one is installed; host-only, no device call."""
+    have_real = subprocess.run(["g++", "-std=c++17", "-E", "-x", "c++", "-"], input="#include <Eigen/Dense>\n", text=True,
+                               capture_output=True, env=_env()).returncode == 0
+    inc = ["-I", INC] + ([] if have_real else ["-I", os.path.join(ROOT, "tests", "cpp", "eigen_stub")])
+    exe = str(tmp_path / "test_eigen_adapters")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", *inc, os.path.join(ROOT, "tests", "cpp", "test_eigen_adapters.cpp"),
+                           "-o", exe, "-L", LIBDIR, "-lcilantro_b200", f"-Wl,-rpath,{LIBDIR}"], env=_env())
+    assert subprocess.run([exe]).returncode == 0
+
+
 def test_example_program_compiles():
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", INC,
                            os.path.join(ROOT, "examples", "register_clouds.cpp")], env=_env())
