@@ -90,10 +90,13 @@ __device__ __forceinline__ Rigid rigid_from_t12_dev(const float* T12) {
   return r;
 }
 
-// The serial epilogue of an iteration (one thread): totals -> update -> new state. Kept out of line so that its
-// double-precision temporaries do not set the register count of the search kernel.
+// The serial epilogue of an iteration (one thread): totals -> update -> new state. It runs in a kernel of its own
+// (icp_finish_kernel, one warp): inside the search kernel its temporaries were spilled at that kernel's register
+// budget, and a spilled word of ONE thread lives in its own 128-byte line of local memory - after a 10 M-point pass
+// every one of them was a cold DRAM miss (%globaltimer trace: 47 us per solve at 10 M, 12 us at 1 M, for ~2 us of
+// arithmetic).
 template <int MODE>
-__device__ __noinline__ void loop_solve(const LoopArgs* ap, const BlockCtx* cxp, const double* s, int late,
+__device__ __forceinline__ void loop_solve(const LoopArgs* ap, const BlockCtx* cxp, const double* s, int late,
                                         unsigned long long seq) {
   const LoopArgs& a = *ap;
   const BlockCtx& cx = *cxp;
@@ -343,6 +346,185 @@ __global__ void __launch_bounds__(kBlock, CB_WARM_MIN_BLOCKS) icp_cached_kernel(
   if (lane < NV) a.rs.result[32 + lane] = tot;
 }
 
+// ---- the cached pass, asynchronous-copy pipeline (the shipped version) ---------------------------------------------------
+// Same arithmetic, same tile walk, same flags and sums as icp_cached_kernel above; what changes is how the data gets
+// to the thread. ncu on the register version (profiles/r02_icp_cached_kernel.md): 128 registers -> 2 blocks/SM, 24 %
+// of the warp slots occupied, long-scoreboard the top stall, 27 % of the DRAM bandwidth - each thread can only keep
+// the loads in flight that it has registers for. Here every thread runs a private three-deep pipeline of
+// cp.async copies into shared memory (LDGSTS: no destination register, no scoreboard slot):
+//   stage A (tile k+2)  the streamed arrays: its queries' point (16 B), exclusion radius (4 B), cached match (4 B)
+//   stage B (tile k+1)  the gathers, once A has landed: the matched destination point (+ normal for the plane term)
+//   stage C (tile k)    evaluation from shared memory
+// Each thread only ever reads what it copied itself, so cp.async.wait_group is all the synchronisation there is -
+// no block barrier inside the tile loop. Tiles are kPipeQpt x 256 queries (2 per thread): three A buffers and two B
+// buffers are 52 KB (p2p) / 68 KB (combined) per block, 4 / 3 blocks per SM.
+constexpr int kPipeQpt = 2;
+constexpr int kPipeTile = kPipeQpt * kBlock;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_16_cg(void* dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16_ca(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool kNormals>
+struct PipeSmem {
+  float4 src[3][kPipeTile];
+  float r[3][kPipeTile];
+  int seed[3][kPipeTile];
+  float4 pt[2][kPipeTile];
+  float4 nr[kNormals ? 2 : 1][kNormals ? kPipeTile : 1];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock, (MODE == kModeCombined) ? 3 : 4) icp_cached_pipe_kernel(const __grid_constant__ LoopArgs a) {
+  constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
+  constexpr bool kNormals = (MODE == kModeCombined);
+  extern __shared__ __align__(16) unsigned char pipe_raw[];
+  PipeSmem<kNormals>& ps = *reinterpret_cast<PipeSmem<kNormals>*>(pipe_raw);
+  __shared__ BlockCtx cx;
+  __shared__ AsyncReduceSmem<NV> rsm;
+  const unsigned int tid = threadIdx.x, lane = tid & 31u;
+  const uint32_t ntiles = (a.n_src + kPipeTile - 1) / kPipeTile;
+  const bool want_nrm = kNormals && a.has_pl != 0;
+
+  // stage A of tile `tile` into buffer `buf`: nothing here depends on the loop state
+  auto stage_a = [&](uint32_t tile, int buf) {
+    if (tile < ntiles) {
+#pragma unroll
+      for (int k = 0; k < kPipeQpt; k++) {
+        const uint32_t slot = k * kBlock + tid, i = tile * kPipeTile + slot;
+        if (i < a.n_src) {
+          cp_async_16_cg(&ps.src[buf][slot], a.src_pts + i);
+          cp_async_4(&ps.r[buf][slot], a.cache_r + i);
+          cp_async_4(&ps.seed[buf][slot], a.cache_pos + i);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+  // stage B: the gathers of tile `tile` (its stage A has landed in abuf) into bbuf
+  auto stage_b = [&](uint32_t tile, int abuf, int bbuf) {
+    if (tile < ntiles) {
+#pragma unroll
+      for (int k = 0; k < kPipeQpt; k++) {
+        const uint32_t slot = k * kBlock + tid, i = tile * kPipeTile + slot;
+        if (i < a.n_src) {
+          const int sd = ps.seed[abuf][slot];
+          if (sd >= 0 && ps.r[abuf][slot] > 0.f) {
+            cp_async_16_ca(&ps.pt[bbuf][slot], a.dst.pts + sd);
+            if (kNormals && want_nrm) cp_async_16_ca(&ps.nr[bbuf][slot], a.dst.nrm + sd);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  const uint32_t t0 = blockIdx.x, stride = gridDim.x;
+  stage_a(t0, 0);           // group: A(0)
+  stage_a(t0 + stride, 1);  // group: A(1)
+  if (tid == 0) {
+    rsm.arrived = 0u;
+    load_block_ctx(a, cx);
+  }
+  __syncthreads();
+  if (cx.done) {
+    cp_async_wait<0>();
+    return;
+  }
+  if (a.trace && blockIdx.x == 0 && tid == 0) {
+    const int slot = __ldcg(&a.st->iters) & 63;
+    a.st->trace[slot][0] = global_timer_ns();
+    a.st->trace[slot][4] = 0ull;
+  }
+  cp_async_wait<1>();   // A(0) has landed
+  stage_b(t0, 0, 0);    // group: B(0)
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; v++) acc[v] = 0.0;
+  // iteration n evaluates tile t0 + n*stride; on entry the committed groups are ... A(n+1), B(n)
+  int abuf = 0, bbuf = 0;
+#pragma unroll 1
+  for (uint32_t tile = t0; tile < ntiles; tile += stride) {
+    const int abuf1 = (abuf == 2) ? 0 : abuf + 1, abuf2 = (abuf1 == 2) ? 0 : abuf1 + 1;
+    stage_a(tile + 2 * stride, abuf2);             // group: A(n+2)
+    cp_async_wait<2>();                            // pending at most {B(n), A(n+2)}: A(n+1) has landed
+    stage_b(tile + stride, abuf1, bbuf ^ 1);       // group: B(n+1)
+    cp_async_wait<2>();                            // pending at most {A(n+2), B(n+1)}: B(n) has landed
+    const uint32_t base = tile * kPipeTile;
+#pragma unroll
+    for (int k = 0; k < kPipeQpt; k++) {
+      const uint32_t slot = k * kBlock + tid, i = base + slot;
+      const bool active = i < a.n_src;
+      bool miss = active;
+      if (active) {
+        const float rc = ps.r[abuf][slot];
+        const int sd = ps.seed[abuf][slot];
+        if (rc > 0.f) {
+          const float4 sc = ps.src[abuf][slot];
+          float qx, qy, qz, ox, oy, oz;
+          apply_rigid(cx.T, sc.x, sc.y, sc.z, qx, qy, qz);
+          apply_rigid(cx.Tp, sc.x, sc.y, sc.z, ox, oy, oz);
+          const float ex = __fsub_rn(qx, ox), ey = __fsub_rn(qy, oy), ez = __fsub_rn(qz, oz);
+          // upper bound of the distance the query moved since the previous iteration
+          const float dl = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex)))), kUp18);
+          const float r2 = __fsub_rd(rc, dl);
+          if (r2 > 0.f) {
+            // every reference point other than `seed` has a computed d2 above lim under the current transform
+            const float lim = __fmul_rd(__fmul_rd(r2, r2), kDown17);
+            bool pair = false;
+            float d2 = 0.f;
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sd >= 0) {
+              p = ps.pt[bbuf][slot];
+              const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+              d2 = __fmul_rn(dx, dx);
+              d2 = __fadd_rn(d2, __fmul_rn(dy, dy));
+              d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
+              if (d2 < a.max_d2) {
+                if (d2 < lim) {  // still the unique nearest neighbour, inside the radius
+                  miss = false;
+                  pair = true;
+                }
+              } else if (a.max_d2 <= lim) {  // the match left the radius and nothing else is inside it
+                miss = false;
+              }
+            } else if (a.max_d2 <= lim) {  // nothing was within the radius and nothing can have entered it
+              miss = false;
+            }
+            if (!miss) a.cache_r[i] = r2;
+            if (pair) {
+              accumulate_pair<MODE, true>(
+                  acc, cx, a.has_pt != 0, a.has_pl != 0, p, qx, qy, qz, a.src_nrm != nullptr,
+                  [&] { return kNormals ? ps.nr[kNormals ? bbuf : 0][kNormals ? slot : 0] : make_float4(0.f, 0.f, 0.f, 0.f); },
+                  [&] { return __ldg(a.src_nrm + i); }, d2);
+            }
+          }
+        }
+      }
+      const unsigned int mm = __ballot_sync(0xffffffffu, miss);
+      if (lane == 0 && (base + k * kBlock + (tid & ~31u)) < a.n_src) a.miss_mask[(base + k * kBlock + tid) >> 5] = mm;
+    }
+    abuf = abuf1;
+    bbuf ^= 1;
+  }
+  cp_async_wait<0>();
+  double tot = 0;
+  if (!grid_reduce_async_tail<NV>(acc, a.rs, rsm, tot)) return;
+  if (lane < NV) a.rs.result[32 + lane] = tot;
+}
+
 #ifndef CB_LOOP_MIN_BLOCKS
 #define CB_LOOP_MIN_BLOCKS 4
 #endif
@@ -457,10 +639,28 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
     // ---- reduction ----------------------------------------------------------------------------------------------------
     if (!grid_reduce_async_tail<NV>(acc, a.rs, rsm, tot)) return;
   }
-  // the last warp of the grid adds the cached pass, exchanges, solves and publishes the next transform
-  if (!kCold && lane < NV) tot += __ldcg(a.rs.result + 32 + lane);  // totals of the cached pass (fixed order: search + cached)
-  bool late = false;
+  // the last warp of the grid adds the cached pass's totals and hands this GPU's sums to icp_finish_kernel
+  if (!kCold && lane < NV) tot += __ldcg(a.rs.result + 32 + lane);  // fixed order: search + cached
+  if (lane < NV) a.rs.result[lane] = tot;
   if (a.trace && lane == 0) a.st->trace[trace_slot][1] = global_timer_ns();
+}
+
+// ---- kernel 3 of an iteration: exchange + solve (one warp) -------------------------------------------------------------
+// This GPU's totals -> all-reduce with the peer ranks over NVLink peer memory (reduce.cuh, bounded wait; every rank
+// sums the rows in rank order -> bit-identical totals) -> Kabsch / Gauss-Newton step, rotation(), compose,
+// convergence test -> LoopState for the next iteration's kernels.
+template <int MODE>
+__global__ void __launch_bounds__(32, 1) icp_finish_kernel(const __grid_constant__ LoopArgs a) {
+  constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
+  __shared__ BlockCtx cx;
+  __shared__ double sbuf[kCombinedValues + 8];
+  const unsigned int lane = threadIdx.x;
+  if (lane == 0) load_block_ctx(a, cx);
+  __syncwarp();
+  if (cx.done) return;
+  const int trace_slot = a.trace ? (__ldcg(&a.st->iters) & 63) : 0;
+  double tot = (lane < NV) ? __ldcg(a.rs.result + lane) : 0.0;
+  bool late = false;
   const unsigned long long seq = __ldcg(&a.st->xseq) + 1ull;
   if (a.rs.ex.enabled && a.rs.ex.world > 1) {
     Exchange ex = a.rs.ex;
@@ -468,11 +668,10 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
     tot = exchange_rows<NV>(tot, ex, (int)lane, &late);
   }
   if (a.trace && lane == 0) a.st->trace[trace_slot][2] = global_timer_ns();
-  double* sbuf = rsm.slot[0];  // every warp of this block has arrived: the slots are free
   if (lane < NV) sbuf[lane] = tot;
   __syncwarp();
   if constexpr (MODE == kModeCombined) {
-    // d_theta = AtA^-1 Atb with the augmented matrix spread over the warp; parked behind the totals (slot[1] is free too)
+    // d_theta = AtA^-1 Atb with the augmented matrix spread over the warp, parked behind the totals
     double x[6];
     solve6_warp(sbuf, (int)lane, x);
     if (lane == 0)
@@ -541,9 +740,25 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
   // iterations: cached pass (kWarmTile queries per block) + search kernel over the flagged queries
   const int blocks_cold = std::max(1, (int)((ns + kBlock - 1) / kBlock));
   const int blocks_search = std::max(1, (int)((ns + (size_t)kQptWarm * kBlock - 1) / ((size_t)kQptWarm * kBlock)));
-  // persistent cached pass: a whole number of resident blocks per SM (never more blocks than tiles)
-  const int cached_per_sm = CB_WARM_MIN_BLOCKS;  // __launch_bounds__ of icp_cached_kernel
-  const int blocks_cached = std::max(1, std::min(ctx->sm_count * cached_per_sm, (int)((ns + kWarmTile - 1) / kWarmTile)));
+  // persistent cached pass: a whole number of resident blocks per SM (never more blocks than tiles).
+  // CB_CACHED_REGS=1 selects the register-staged version (icp_cached_kernel) for A/B measurements.
+  static const bool cached_regs = getenv("CB_CACHED_REGS") != nullptr;
+  const bool p2p = prm->metric == CB_ICP_POINT_TO_POINT;
+  const size_t pipe_smem = p2p ? sizeof(PipeSmem<false>) : sizeof(PipeSmem<true>);
+  int blocks_cached;
+  if (cached_regs) {
+    blocks_cached = std::max(1, std::min(ctx->sm_count * CB_WARM_MIN_BLOCKS, (int)((ns + kWarmTile - 1) / kWarmTile)));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CB_CUDA(cudaFuncSetAttribute(icp_cached_pipe_kernel<kModeP2PCentered>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(PipeSmem<false>)));
+      CB_CUDA(cudaFuncSetAttribute(icp_cached_pipe_kernel<kModeCombined>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(PipeSmem<true>)));
+      attr_set = true;
+    }
+    blocks_cached = std::max(1, std::min(ctx->sm_count * (p2p ? 4 : 3), (int)((ns + kPipeTile - 1) / kPipeTile)));
+  }
   CB_TRY(get_reduce_scratch(ctx, blocks_cold, kMaxValues, &a.rs));
   if (!icp->d_miss_mask) CB_CUDA(cudaMalloc(&icp->d_miss_mask, (ns / 32 + 2) * sizeof(uint32_t)));
   a.miss_mask = icp->d_miss_mask;
@@ -582,18 +797,28 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
         if (cold) {
           icp_search_kernel<kModeP2PCentered, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
         } else {
-          icp_cached_kernel<kModeP2PCentered><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          if (cached_regs)
+            icp_cached_kernel<kModeP2PCentered><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          else
+            icp_cached_pipe_kernel<kModeP2PCentered><<<blocks_cached, kBlock, pipe_smem, ctx->stream>>>(a);
           icp_search_kernel<kModeP2PCentered, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
         }
       } else {
         if (cold) {
           icp_search_kernel<kModeCombined, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
         } else {
-          icp_cached_kernel<kModeCombined><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          if (cached_regs)
+            icp_cached_kernel<kModeCombined><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
+          else
+            icp_cached_pipe_kernel<kModeCombined><<<blocks_cached, kBlock, pipe_smem, ctx->stream>>>(a);
           icp_search_kernel<kModeCombined, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
         }
       }
-      ctx->launches += cold ? 0 : 1;
+      if (prm->metric == CB_ICP_POINT_TO_POINT)
+        icp_finish_kernel<kModeP2PCentered><<<1, 32, 0, ctx->stream>>>(a);
+      else
+        icp_finish_kernel<kModeCombined><<<1, 32, 0, ctx->stream>>>(a);
+      ctx->launches += cold ? 1 : 2;
       ctx->launches += 1;
       if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k) + 1], ctx->stream));
     }

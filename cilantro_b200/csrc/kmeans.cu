@@ -22,7 +22,10 @@ using namespace cb;
 namespace {
 
 constexpr int kBlock = 256;
-constexpr int kPts = 4;       // points per thread held in registers
+#ifndef CB_KMEANS_PTS
+#define CB_KMEANS_PTS 4
+#endif
+constexpr int kPts = CB_KMEANS_PTS;  // points per thread held in registers
 constexpr int kChunk = 1024;  // centroids staged per shared-memory chunk
 
 // sums layout in global memory: K x 4 doubles (sx, sy, sz, count)
