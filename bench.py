@@ -413,8 +413,11 @@ def icp_bench(args, name, w, scaling, ctx, rank, world, local, with_e2e=True, wi
         return {"achieved": a, "frac": a / peak, "ms": ms}
 
     mean = frac(ms_per_step)
+    tr = load_traffic(name) or {}
     roofline = {"bound": "hbm", "achieved": mean["achieved"], "peak": peak, "unit": "GB/s", "frac": mean["frac"],
-                "traffic": load_traffic(name),
+                # DRAM bytes of one converged iteration's kernels (cached pass + search + finish), ncu --set full
+                "traffic": (tr.get("converged_iteration") or {}).get("total") if world == 1 else None,
+                "traffic_detail": tr if world == 1 else None,
                 "kernel": ("one ICP iteration = icp_cached_kernel<%s> (exact re-use of the previous matches) + "
                            "icp_search_kernel<%s> (grid 1-NN of the remaining queries, reduction, exchange, solve); "
                            "the first iteration of a call is icp_search_kernel alone" % (w["metric"], w["metric"])),

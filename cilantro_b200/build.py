@@ -77,6 +77,10 @@ def build(force=False, verbose=False, defines=(), out=None):
         raise RuntimeError("nvcc failed for: " + ", ".join(os.path.basename(f) for f in failed))
     if jobs or not os.path.exists(target) or any(os.path.getmtime(o) > os.path.getmtime(target) for o in objs):
         subprocess.check_call([nvcc] + LINK_FLAGS + ["-ccbin", "g++", "-o", target] + objs + ["-ldl"], env=_env())
+    if out is not None or defines or verbose:  # experimental variants do not keep their objects around
+        import shutil
+
+        shutil.rmtree(objdir, ignore_errors=True)
     return target
 
 

@@ -735,14 +735,18 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   CB_CHECK(prm->metric == CB_ICP_POINT_TO_POINT || prm->metric == CB_ICP_COMBINED, CB_ERR_INVALID, "bad metric");
   cb_context* ctx = icp->ctx;
   CB_CUDA(cudaSetDevice(ctx->device));
+  int hand_over = 0;
   {
     // Default correspondence engine, one Gauss-Newton step per iteration (the reference's defaults): the
     // device-resident loop (icp_loop.cu). CB_HOST_LOOP=1 keeps the host-driven loop below for A/B measurements;
     // engine modes, inner Gauss-Newton iterations and multi-rank runs without the fused exchange always use it.
     static const bool host_loop = getenv("CB_HOST_LOOP") != nullptr;
     const bool one_step = prm->metric == CB_ICP_POINT_TO_POINT || prm->max_opt_iter == 1;
-    if (!host_loop && !prm->host_loop && !engine_mode(prm) && one_step && (ctx->world == 1 || exchange_available(ctx)))
-      return icp_loop_estimate(icp, prm, res);
+    if (!host_loop && !prm->host_loop && !engine_mode(prm) && one_step && (ctx->world == 1 || exchange_available(ctx))) {
+      const int rc = icp_loop_estimate(icp, prm, res, &hand_over);
+      if (rc != CB_OK || !hand_over) return rc;
+      // the run is not converging: continue from the device loop's state with the host-driven loop below
+    }
   }
   icp->loop_last = false;
   const uint64_t launches0 = ctx->launches;
@@ -766,6 +770,20 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   icp->nn_valid = false;
   icp->warm_ok = false;
   icp->search_ms = 0;
+  const uint64_t loop_launches = hand_over ? res->kernel_launches : 0;
+  std::vector<double> loop_iter_ms;
+  if (hand_over) {
+    // continue the device loop's run: its transform, its iteration count, its matches as warm seeds
+    // (d_nn_pos holds sorted dst positions or -1 there too)
+    std::memcpy(T, res->T, sizeof(T));
+    iters = res->iterations;
+    last_delta = res->last_delta;
+    n_corr = (double)res->num_corr;
+    icp->nn_valid = true;
+    icp->warm_ok = true;
+    loop_iter_ms = icp->iter_ms;
+  }
+  const int iters0 = iters;
   while (iters < max_iter) {  // icp_base.hpp:76-84
     if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
     cudaEvent_t e0 = timing ? icp->events[2 * iters] : nullptr, e1 = timing ? icp->events[2 * iters + 1] : nullptr;
@@ -786,7 +804,12 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   CB_CUDA(cudaStreamSynchronize(ctx->stream));
   icp->iter_ms.assign(iters, 0.0);
   double total = 0;
-  for (int i = 0; i < iters && timing != 0; i++) {
+  for (int i = 0; i < iters0 && i < (int)loop_iter_ms.size(); i++) {  // the device loop's share of a handed-over run
+    icp->iter_ms[i] = loop_iter_ms[i];
+    total += loop_iter_ms[i];
+    if (timing == 2) icp->search_ms += loop_iter_ms[i];
+  }
+  for (int i = iters0; i < iters && timing != 0; i++) {
     float ms = 0.f;
     CB_CUDA(cudaEventElapsedTime(&ms, icp->events[2 * i], icp->events[2 * i + 1]));
     if (timing == 1) {
@@ -814,7 +837,7 @@ int cb_icp_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
   res->num_corr = (uint64_t)(n_corr + 0.5);
   res->gpu_ms_total = total;
   res->gpu_ms_search = icp->search_ms;
-  res->kernel_launches = ctx->launches - launches0;
+  res->kernel_launches = ctx->launches - launches0 + loop_launches;
   return CB_OK;
 }
 

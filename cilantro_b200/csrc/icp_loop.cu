@@ -654,19 +654,26 @@ __global__ void __launch_bounds__(32, 1) icp_finish_kernel(const __grid_constant
   constexpr int NV = (MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
   __shared__ BlockCtx cx;
   __shared__ double sbuf[kCombinedValues + 8];
+  static_assert(NV + 2 <= kExchangeVals, "row of the fused exchange");
   const unsigned int lane = threadIdx.x;
   if (lane == 0) load_block_ctx(a, cx);
   __syncwarp();
   if (cx.done) return;
   const int trace_slot = a.trace ? (__ldcg(&a.st->iters) & 63) : 0;
+  // lanes < NV: the moments; lane NV: queries this rank searched in this iteration; lane NV + 1: its source points
+  // (both ride along so that every rank sees the same global search share: the hand-over decision of the host)
   double tot = (lane < NV) ? __ldcg(a.rs.result + lane) : 0.0;
+  if (lane == NV) tot = (double)__ldcg(&a.st->searched_cur);
+  if (lane == NV + 1) tot = (double)a.n_src;
   bool late = false;
   const unsigned long long seq = __ldcg(&a.st->xseq) + 1ull;
   if (a.rs.ex.enabled && a.rs.ex.world > 1) {
     Exchange ex = a.rs.ex;
     ex.seq = seq;  // executed passes are numbered on the device: launches skipped after convergence take no number
-    tot = exchange_rows<NV>(tot, ex, (int)lane, &late);
+    tot = exchange_rows<NV + 2>(tot, ex, (int)lane, &late);
   }
+  if (lane == NV) a.st->searched_all = tot;
+  if (lane == NV + 1) a.st->queries_all = tot;
   if (a.trace && lane == 0) a.st->trace[trace_slot][2] = global_timer_ns();
   if (lane < NV) sbuf[lane] = tot;
   __syncwarp();
@@ -684,7 +691,8 @@ __global__ void __launch_bounds__(32, 1) icp_finish_kernel(const __grid_constant
 
 }  // namespace
 
-int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res) {
+int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res, int* hand_over) {
+  *hand_over = 0;
   cb_context* ctx = icp->ctx;
   const uint64_t launches0 = ctx->launches;
   const int max_iter = std::max(prm->max_iter, 0);
@@ -786,9 +794,15 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
     const char* e = getenv("CB_LOOP_BATCH");
     return e ? std::max(1, atoi(e)) : 16;
   }();
+  // The first batch is short: by its end a converging run searches a fraction of a percent of its queries per
+  // iteration; a run that still searches more than kGiveUpShare of them is handed over to the host-driven loop
+  // (the exclusion cache costs more than it saves there). CB_LOOP_NO_HANDOVER=1 keeps the device loop regardless.
+  static const bool no_handover = getenv("CB_LOOP_NO_HANDOVER") != nullptr;
+  constexpr int kFirstBatch = 4;
+  constexpr double kGiveUpShare = 0.15;
   bool finished = (max_iter == 0);
   while (!finished) {
-    const int n = std::min(kBatch, max_iter - issued);
+    const int n = std::min(issued == 0 ? kFirstBatch : kBatch, max_iter - issued);
     for (int k = 0; k < n; ++k) {
       if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
       if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k)], ctx->stream));
@@ -827,6 +841,10 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res)
     CB_CUDA(cudaMemcpyAsync(hs, icp->d_state, sizeof(*hs), cudaMemcpyDeviceToHost, ctx->stream));
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
     finished = hs->done != 0 || issued >= max_iter;
+    if (!finished && !no_handover && hs->iters >= kFirstBatch && hs->searched_all > kGiveUpShare * hs->queries_all) {
+      *hand_over = 1;
+      finished = true;
+    }
   }
   if (max_iter == 0) CB_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->seq = hs->xseq;

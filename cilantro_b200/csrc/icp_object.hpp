@@ -23,6 +23,8 @@ struct LoopState {
   double n_corr;      // correspondences of the last executed iteration (all ranks)
   unsigned long long searched_cur;   // queries searched so far by the running iteration (this rank)
   unsigned long long searched_last;  // ... by the last executed iteration
+  double searched_all;               // the same over ALL ranks (exchanged with the moments: identical everywhere)
+  double queries_all;                // source points of all ranks
   double sums[32];    // its reduced moments / normal equations (all ranks)
   // CB_LOOP_TRACE=1: per executed iteration (mod 64): %globaltimer at kernel start / local reduction done /
   // peers' rows summed / state written, the number of queries that needed a search, %globaltimer at the start of
@@ -61,6 +63,9 @@ struct cb_icp {
 namespace cb {
 // cb_icp_estimate for the default correspondence engine with one Gauss-Newton step per iteration: all iterations
 // enqueued back to back, transform kept on the device (icp_loop.cu).
-int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res);
+// *hand_over = 1: the loop stopped after res->iterations iterations because the cache was not paying (the run is not
+// converging: a large share of the queries is searched again every iteration); the caller continues from res with the
+// host-driven loop, whose plain search is cheaper per searched query.
+int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res, int* hand_over);
 unsigned long long exchange_timeout_ns();
 }  // namespace cb

@@ -130,28 +130,47 @@ def downsample_launches(csv_path, out_path, rnd):
 
 
 def main():
-    rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    rnd = sys.argv[1] if len(sys.argv) > 1 else "r02"
     dl = os.path.join(OUT, f"launches_downsample_{rnd}.csv")
     if os.path.exists(dl):
         downsample_launches(dl, os.path.join(HERE, f"{rnd}_downsample_launches.md"), rnd)
         print("wrote downsample launches")
+    flush = "L2 flushed before the iteration (as in bench.py's value leg)."
+    # (report, summary file, title, note, traffic key = (workload, regime part))
     jobs = [
-        (f"prof_{rnd}f.ncu-rep", f"{rnd}_icp_pass_kernel.md", "icp_pass_kernel<p2p, search> — bench.py icp_p2p_1m",
-         "1 M -> 1 M point-to-point ICP iteration (fused transform + warp-pooled grid 1-NN + Kabsch moments), L2 flushed before the launch.",
-         "icp_p2p_1m"),
-        (f"prof_{rnd}_kmeans.ncu-rep", f"{rnd}_kmeans_assign_kernel.md", "kmeans_assign_kernel — bench.py kmeans_5m",
-         "5 M points x 256 centroids, fused assignment + per-cluster double sums (shared-memory atomics).", None),
-        (f"prof_{rnd}_ransac.ncu-rep", f"{rnd}_ransac_score_kernel.md", "ransac_score_kernel — bench.py ransac_500k",
-         "500 k correspondences x 256 hypotheses per launch, inlier counts only.", None),
-        (f"prof_{rnd}_moments.ncu-rep", f"{rnd}_moments_kernel.md", "moments_kernel — bench.py pca_50m",
-         "50 M points, one streaming pass (mean + covariance moments in double).", None),
-        (f"normals_knn_{rnd}.ncu-rep", f"{rnd}_normals_knn_kernel.md", "normals_knn_kernel<16> — bench.py normals_1m",
-         "1 M-point noisy sheet, k = 10: k-best grid search + neighbourhood covariance + 3x3 Jacobi eigen-solve per point.", None),
+        (f"{rnd}_icp_cold_p2p_1m.ncu-rep", f"{rnd}_icp_search_kernel_cold_p2p_1m.md",
+         "icp_search_kernel<p2p, 1, cold> - first iteration of an estimate() call, 1 M -> 1 M",
+         "Every query is searched (nothing cached): transform + warp-pooled WIDE grid 1-NN (exclusion bound for the cache) + "
+         "pivoted Kabsch moments + block/grid reduction. " + flush, ("icp_p2p_1m", "first_iteration", "search")),
+        (f"{rnd}_icp_cached_p2p_1m.ncu-rep", f"{rnd}_icp_cached_pipe_kernel_p2p_1m.md",
+         "icp_cached_pipe_kernel<p2p> - cached pass of a converged iteration, 1 M -> 1 M",
+         "Per query: point + cache streamed, cached match gathered (cp.async pipeline through shared memory), exclusion test, "
+         "moments of the pairs that pass; the rest flagged for the search kernel. " + flush, ("icp_p2p_1m", "converged_iteration", "cached")),
+        (f"{rnd}_icp_warm_search_p2p_1m.ncu-rep", f"{rnd}_icp_search_kernel_warm_p2p_1m.md",
+         "icp_search_kernel<p2p, 16, warm> - search kernel of a converged iteration, 1 M -> 1 M",
+         "Tiles of 4096 queries; a handful of flagged queries in the whole cloud: almost every block only contributes a zero row. "
+         + flush, ("icp_p2p_1m", "converged_iteration", "search")),
+        (f"{rnd}_icp_finish_p2p_1m.ncu-rep", f"{rnd}_icp_finish_kernel_p2p_1m.md",
+         "icp_finish_kernel<p2p> - exchange + solve, one warp", "Totals -> (peer all-reduce when world > 1) -> Kabsch, rotation(), "
+         "compose, convergence test -> LoopState.", ("icp_p2p_1m", "converged_iteration", "finish")),
+        (f"{rnd}_icp_cold_combined_10m.ncu-rep", f"{rnd}_icp_search_kernel_cold_combined_10m.md",
+         "icp_search_kernel<combined, 1, cold> - first iteration, 10 M -> 10 M (BASELINE config 3 on one GPU)",
+         "As above with the 28-value Gauss-Newton normal equations (point + plane terms). " + flush,
+         ("icp_combined_10m", "first_iteration", "search")),
+        (f"{rnd}_icp_cached_combined_10m.ncu-rep", f"{rnd}_icp_cached_pipe_kernel_combined_10m.md",
+         "icp_cached_pipe_kernel<combined> - cached pass of a converged iteration, 10 M -> 10 M",
+         "560 MB algorithmic (16 B point + 8 B cache + 16 B match + 16 B normal per query). " + flush,
+         ("icp_combined_10m", "converged_iteration", "cached")),
+        (f"{rnd}_icp_warm_search_combined_10m.ncu-rep", f"{rnd}_icp_search_kernel_warm_combined_10m.md",
+         "icp_search_kernel<combined, 16, warm> - search kernel of a converged iteration, 10 M -> 10 M",
+         "2442 tiles, a few hundred flagged queries. " + flush, ("icp_combined_10m", "converged_iteration", "search")),
+        (f"{rnd}_kmeans_50m.ncu-rep", f"{rnd}_kmeans_assign_kernel.md", "kmeans_assign_kernel - bench.py kmeans_50m (BASELINE config 4)",
+         "50 M points x 1024 centroids, the shipped kernel with its occupancy-sized persistent grid: fused assignment + "
+         "per-cluster double sums (shared-memory atomics).", None),
+        (f"{rnd}_ransac_5m.ncu-rep", f"{rnd}_ransac_score_kernel.md", "ransac_score_kernel - bench.py ransac_5m (BASELINE config 5)",
+         "5 M correspondences x 1000 hypotheses per launch, inlier counts only.", None),
     ]
     traffic = {}
-    tpath = os.path.join(HERE, "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
     for rep, md, title, note, key in jobs:
         p = os.path.join(OUT, rep)
         if not os.path.exists(p):
@@ -159,17 +178,21 @@ def main():
         text, tr = summarize(p, title, note)
         open(os.path.join(HERE, md), "w").write(text)
         if key and tr:
-            traffic[key] = tr
-            traffic["source"] = f"profiles/{md}"
+            w, regime, part = key
+            traffic.setdefault(w, {}).setdefault(regime, {})[part] = tr
         print("wrote", md)
-    json.dump(traffic, open(tpath, "w"), indent=1)
+    for w, regs in traffic.items():
+        for regime in list(regs):
+            regs[regime]["total"] = sum(v for k, v in regs[regime].items() if k != "total")
+    traffic["source"] = f"profiles/{rnd}_icp_*.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    json.dump(traffic, open(os.path.join(HERE, "traffic.json"), "w"), indent=1)
     lp = os.path.join(OUT, f"launches_{rnd}.csv")
     if os.path.exists(lp):
         shutil.copy(lp, os.path.join(HERE, f"launches_{rnd}.csv"))
         open(os.path.join(HERE, f"launches_{rnd}.md"), "w").write(
-            f"# Launch list of one `bench.py --steps 5 --warmup 3` run ({rnd})\n\n`ncu --metrics gpu__time_duration.sum "
-            "--clock-control none` — cold-cache, serialised: compare SHARES, not absolutes. The run contains the value leg\n"
-            "(8 ICP iterations), three end-to-end calls (45 iterations + 6 grid builds) and the initial grid builds.\n\n"
+            f"# Launch list of one `bench.py --no-secondary --no-cpu-baseline` run ({rnd})\n\n`ncu --metrics gpu__time_duration.sum "
+            "--clock-control none` - cold-cache, serialised: compare SHARES, not absolutes. The run contains the grid builds, the\n"
+            "warm-up and timed estimate() calls of both poses, the clock-sampler filler iterations and three end-to-end calls.\n\n"
             + launches(lp) + "\n")
         print("wrote launches")
 

@@ -123,3 +123,25 @@ def test_rbf_weights_with_inner_gauss_newton_steps_and_engine_mode(cb, ctx, orc)
         want = orc.icp(dst, src, knn, dst_n=nrm, **base, **extra)
         assert got["num_corr"] == want["num_corr"], extra
         assert frob(got["T"], want["T"]) < 1e-5, (extra, frob(got["T"], want["T"]))
+
+
+def test_non_converging_run_is_handed_over_to_the_host_loop(cb, ctx):
+    """A pose outside ICP's basin (SURVEY 8d's fixed 0.02 rad on a dense cloud): a third of the queries is searched
+    again in every iteration, the exclusion cache does not pay, and after its first batch the device loop hands the run
+    over to the host-driven loop - same iterations, same correspondences, same transform as the host loop alone."""
+    n = 300000
+    dst, src, _, _ = synth.icp_pair(n, seed=4, noise=0.001, T_ref=synth.t_ref_default())
+    icp = cb.Icp(ctx, cb.Cloud(ctx, dst), cb.Cloud(ctx, src))
+    kw = dict(metric="p2p", max_iter=9, tol=0.0, max_d2=np.float32(0.02**2))
+    a = icp.estimate(host_loop=True, **kw)
+    b = icp.estimate(host_loop=False, **kw)
+    assert a["iterations"] == b["iterations"] == 9 and a["num_corr"] == b["num_corr"]
+    assert frob(a["T"], b["T"]) < 1e-6
+    assert len(b["iter_ms"]) == 9 and np.all(b["iter_ms"] > 0)
+    with pytest.raises(cb.CbError):  # the run did not END on the device loop: there is no loop cache to inspect
+        icp.loop_cache()
+    # a converging run on the same object afterwards stays on the device loop
+    dst2, src2, _, _ = _pair(n, 4, normals=False)
+    icp2 = cb.Icp(ctx, cb.Cloud(ctx, dst2), cb.Cloud(ctx, src2))
+    icp2.estimate(**kw)
+    assert icp2.loop_cache()[2] < n // 4
