@@ -203,6 +203,14 @@ __device__ __noinline__ void search_chunk_far(const LoopArgs* ap, const BlockCtx
   *out = search_chunk_body<false>(*ap, *cxp, wsm, queue, c, total, base);
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute may
+// be scheduled while its predecessor in the stream is still running; it must execute pdl_wait() before it touches
+// anything the predecessor (or, transitively, earlier kernels: the predecessor passed its own pdl_wait first) wrote.
+// The predecessor allows that early scheduling with pdl_launch_dependents(). Used between the three kernels of an
+// iteration so that the launch latency of the next kernel overlaps the tail of the previous one.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // thread 0 of a block: LoopState -> shared BlockCtx
 __device__ __forceinline__ void load_block_ctx(const LoopArgs& a, BlockCtx& cx) {
   cx.done = __ldcg(&a.st->done);
@@ -432,8 +440,14 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeCombined) ? 3 : 4) icp_c
   };
 
   const uint32_t t0 = blockIdx.x, stride = gridDim.x;
+  // (No pdl_launch_dependents() here: released early, the search kernel's blocks were handed to whichever SMs finished
+  // their share of this pass first - a few SMs ended up with all of its tiles, and iterations that still search many
+  // queries ran 25 % slower.)
+  // The streamed arrays were last written by the PREVIOUS iteration's cached / search kernels, which completed before
+  // the finish kernel this launch depends on even started: they may be requested before the dependency wait.
   stage_a(t0, 0);           // group: A(0)
   stage_a(t0 + stride, 1);  // group: A(1)
+  pdl_wait();               // LoopState (written by the previous iteration's finish kernel)
   if (tid == 0) {
     rsm.arrived = 0u;
     load_block_ctx(a, cx);
@@ -549,6 +563,8 @@ __global__ void __launch_bounds__(kBlock, CB_LOOP_MIN_BLOCKS) icp_search_kernel(
   const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t base = blockIdx.x * kTile;
   unsigned int total = 0;
+  pdl_wait();               // masks, cached totals and cache updates of the cached pass (state of the previous finish)
+  pdl_launch_dependents();  // the one-warp finish kernel may be scheduled now and wait for this grid to drain
   if (tid == 0) {
     rsm.arrived = 0u;
     load_block_ctx(a, cx);
@@ -656,6 +672,8 @@ __global__ void __launch_bounds__(32, 1) icp_finish_kernel(const __grid_constant
   __shared__ double sbuf[kCombinedValues + 8];
   static_assert(NV + 2 <= kExchangeVals, "row of the fused exchange");
   const unsigned int lane = threadIdx.x;
+  pdl_wait();               // this GPU's totals (search kernel), the state of the previous iteration
+  pdl_launch_dependents();  // the next iteration's cached pass may start streaming
   if (lane == 0) load_block_ctx(a, cx);
   __syncwarp();
   if (cx.done) return;
@@ -690,6 +708,24 @@ __global__ void __launch_bounds__(32, 1) icp_finish_kernel(const __grid_constant
 }
 
 }  // namespace
+
+// launch with programmatic stream serialization (see pdl_wait above); CB_NO_PDL=1 falls back to plain launches
+template <class Kernel>
+static cudaError_t launch_pdl(Kernel k, int blocks, int threads, size_t smem, cudaStream_t stream, const LoopArgs& a) {
+  static const bool no_pdl = getenv("CB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  std::memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, k, a);
+}
 
 int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res, int* hand_over) {
   *hand_over = 0;
@@ -809,29 +845,29 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
       const bool cold = (issued + k == 0);
       if (prm->metric == CB_ICP_POINT_TO_POINT) {
         if (cold) {
-          icp_search_kernel<kModeP2PCentered, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
+          CB_CUDA(launch_pdl(icp_search_kernel<kModeP2PCentered, 1, true>, blocks_cold, kBlock, 0, ctx->stream, a));
         } else {
           if (cached_regs)
             icp_cached_kernel<kModeP2PCentered><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
           else
-            icp_cached_pipe_kernel<kModeP2PCentered><<<blocks_cached, kBlock, pipe_smem, ctx->stream>>>(a);
-          icp_search_kernel<kModeP2PCentered, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
+            CB_CUDA(launch_pdl(icp_cached_pipe_kernel<kModeP2PCentered>, blocks_cached, kBlock, pipe_smem, ctx->stream, a));
+          CB_CUDA(launch_pdl(icp_search_kernel<kModeP2PCentered, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
         }
       } else {
         if (cold) {
-          icp_search_kernel<kModeCombined, 1, true><<<blocks_cold, kBlock, 0, ctx->stream>>>(a);
+          CB_CUDA(launch_pdl(icp_search_kernel<kModeCombined, 1, true>, blocks_cold, kBlock, 0, ctx->stream, a));
         } else {
           if (cached_regs)
             icp_cached_kernel<kModeCombined><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
           else
-            icp_cached_pipe_kernel<kModeCombined><<<blocks_cached, kBlock, pipe_smem, ctx->stream>>>(a);
-          icp_search_kernel<kModeCombined, kQptWarm, false><<<blocks_search, kBlock, 0, ctx->stream>>>(a);
+            CB_CUDA(launch_pdl(icp_cached_pipe_kernel<kModeCombined>, blocks_cached, kBlock, pipe_smem, ctx->stream, a));
+          CB_CUDA(launch_pdl(icp_search_kernel<kModeCombined, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
         }
       }
       if (prm->metric == CB_ICP_POINT_TO_POINT)
-        icp_finish_kernel<kModeP2PCentered><<<1, 32, 0, ctx->stream>>>(a);
+        CB_CUDA(launch_pdl(icp_finish_kernel<kModeP2PCentered>, 1, 32, 0, ctx->stream, a));
       else
-        icp_finish_kernel<kModeCombined><<<1, 32, 0, ctx->stream>>>(a);
+        CB_CUDA(launch_pdl(icp_finish_kernel<kModeCombined>, 1, 32, 0, ctx->stream, a));
       ctx->launches += cold ? 1 : 2;
       ctx->launches += 1;
       if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k) + 1], ctx->stream));
