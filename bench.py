@@ -354,13 +354,30 @@ def icp_bench(args, name, w, scaling, ctx, rank, world, local, with_e2e=True, wi
         e2e_runs = 3
         barrier(world)
         e2e_t = []
+        from cilantro_b200.dist import shard_bounds
+
+        dlo, dhi = shard_bounds(n_dst, rank, world)  # this rank's block of the replicated destination cloud
+        if world > 1:
+            # check, outside the timed region, that the block-wise replication gives every rank the whole cloud bit for bit
+            chk = capi.Cloud.replicated(ctx, dst[dlo:dhi], nrm[dlo:dhi] if nrm is not None else None, dlo, n_dst)
+            got_p, got_n = chk.download(normals=True) if nrm is not None else (chk.download(), None)
+            assert np.array_equal(got_p.view(np.uint32), dst.view(np.uint32)), "replicated destination cloud differs"
+            assert nrm is None or np.array_equal(got_n.view(np.uint32), nrm.view(np.uint32)), "replicated normals differ"
+            chk.close()
         for _ in range(e2e_runs):
             ctx.synchronize()
             barrier(world)
             t0 = time.perf_counter()
             # what the ICP constructor of the shims does: both clouds in one call (the second upload overlaps the
             # first grid build), then the ICP object (means)
-            c_dst, c_src = capi.cloud_pair(ctx, dst, nrm, src, None, offset_b=lo)
+            if world == 1:
+                c_dst, c_src = capi.cloud_pair(ctx, dst, nrm, src, None, offset_b=lo)
+            else:
+                # every rank uploads ITS block of the destination cloud; the blocks are exchanged over NVLink
+                c_dst = capi.Cloud.replicated(ctx, dst[dlo:dhi], nrm[dlo:dhi] if nrm is not None else None, dlo, n_dst)
+                c_src = capi.Cloud(ctx, src, None, index_offset=lo)
+                c_dst.grid_info()
+                c_src.grid_info()
             t2 = time.perf_counter()
             c_icp = capi.Icp(ctx, c_dst, c_src)
             t3 = time.perf_counter()
@@ -376,11 +393,14 @@ def icp_bench(args, name, w, scaling, ctx, rank, world, local, with_e2e=True, wi
             c_icp.close(); c_src.close(); c_dst.close()
         e2e_s = cdist.max_over_ranks(min(e2e_t))
         e2e_its = e2e_iters / e2e_s
-        h2d = (dst.nbytes + src.nbytes + (nrm.nbytes if nrm is not None else 0)) / e2e_iters
+        dst_up = dst.nbytes + (nrm.nbytes if nrm is not None else 0)
+        h2d = (dst_up * (dhi - dlo) / max(n_dst, 1) + src.nbytes) / e2e_iters  # per rank
         d2h = (48 + 64) / e2e_iters  # the transform + the loop state summary, once per call
         e2e = {"value": e2e_its * n_src_all, "unit": "correspondences/s", "iterations_per_sec": e2e_its,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "what": (f"cb_cloud_create_pair from pinned host buffers (2 uploads + 2 grid builds) + cb_icp_create + "
+               "what": ((f"cb_cloud_create_pair from pinned host buffers (2 uploads + 2 grid builds)" if world == 1 else
+                         f"cb_cloud_create_replicated (each rank uploads 1/{world} of the destination cloud, blocks exchanged "
+                         f"over NVLink) + cb_cloud_create (source shard) + 2 grid builds") + " + cb_icp_create + "
                         f"cb_icp_estimate({e2e_iters} iterations, enqueued back to back, transform kept on the device) + "
                         f"result on host; best of {e2e_runs}; {e2e_s * 1e3:.2f} ms per call")}
 

@@ -90,7 +90,7 @@ EXPORTED = [
     "cb_context_kernel_launches", "cb_context_flush_l2",
     "cb_comm_unique_id", "cb_context_init_comm", "cb_context_comm_info", "cb_comm_ipc_handle", "cb_comm_ipc_attach",
     "cb_comm_ipc_detach",
-    "cb_cloud_create", "cb_cloud_create_pair", "cb_cloud_create_from_device", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
+    "cb_cloud_create", "cb_cloud_create_pair", "cb_cloud_create_from_device", "cb_cloud_create_replicated", "cb_cloud_destroy", "cb_cloud_size", "cb_cloud_grid_info",
     "cb_cloud_estimate_normals", "cb_grid_downsample", "cb_cloud_grid_downsample", "cb_cloud_download",
     "cb_knn1_radius", "cb_knn_radius", "cb_radius_search", "cb_find_correspondences",
     "cb_icp_default_params", "cb_icp_create", "cb_icp_destroy", "cb_icp_estimate", "cb_icp_iteration_times",
@@ -260,6 +260,16 @@ class Cloud:
         _check(lib().cb_cloud_estimate_normals(self.ctx.h, self.h, C.c_int(k), C.c_float(radius2), _p(vp),
                                                C.c_int(int(use_current_as_ref)), _p(nrm), _p(curv), _p(cov), C.byref(ms)))
         return {"normals": nrm, "curvature": curv, "cov6": cov, "gpu_ms": ms.value}
+
+    @classmethod
+    def replicated(cls, ctx, xyz_block, normals_block, first_index, n_total):
+        """cb_cloud_create_replicated: every rank passes its contiguous block; all of them get the whole cloud."""
+        xb = _f32(xyz_block)
+        nb = _f32(normals_block) if normals_block is not None else None
+        h = C.c_void_p()
+        _check(lib().cb_cloud_create_replicated(ctx.h, _p(xb), _p(nb), C.c_size_t(xb.shape[0]), C.c_uint64(first_index),
+                                                C.c_size_t(n_total), C.byref(h)))
+        return cls._wrap(ctx, h)
 
     @classmethod
     def _wrap(cls, ctx, handle):

@@ -415,6 +415,56 @@ int cb_cloud_create_pair(cb_context* ctx, const float* xyz_a, const float* norma
   return CB_OK;
 }
 
+// A cloud every rank needs in full (the destination cloud of a sharded ICP), created from its contiguous blocks: each
+// rank uploads ONLY its block over its own PCIe link, the blocks are exchanged over NVLink (one integer-sum
+// all-reduce of the zero-initialised arrays = an exact all-gather of bit patterns). Replaces N uploads of the whole
+// cloud (N x the PCIe time for the same bytes) when the caller's data is already partitioned - or cheaply sliceable,
+// as in bench.py's end-to-end leg. Collective: every rank of the communicator calls it with the same n_total and
+// the same presence of normals.
+int cb_cloud_create_replicated(cb_context* ctx, const float* xyz_block, const float* normals_block, size_t n_block,
+                               uint64_t first_index, size_t n_total, cb_cloud** out) {
+  CB_CHECK(ctx && out, CB_ERR_INVALID, "null argument");
+  CB_CHECK(n_block == 0 || xyz_block, CB_ERR_INVALID, "xyz is null");
+  CB_CHECK(first_index + n_block <= n_total, CB_ERR_INVALID, "block outside the cloud");
+  CB_CHECK(n_total < (1ull << 31), CB_ERR_INVALID, "point sets of >= 2^31 points are not supported");
+  CB_CUDA(cudaSetDevice(ctx->device));
+  cb_cloud* c = new cb_cloud;
+  c->ctx = ctx;
+  c->n = n_total;
+  c->index_offset = 0;
+  *out = nullptr;
+  auto fail = [&](int rc) {
+    cb_cloud_destroy(c);
+    return rc;
+  };
+  if (n_total > 0) {
+    const size_t words = 3 * n_total;
+    if (cudaMallocAsync(&c->d_raw, words * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+    if (normals_block || ctx->world > 1) {
+      // (with several ranks the presence of normals must be the same everywhere; a rank with an empty block passes
+      // any non-null pointer)
+      if (normals_block && cudaMallocAsync(&c->d_raw_nrm, words * sizeof(float), ctx->stream) != cudaSuccess)
+        return fail(CB_ERR_CUDA);
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+      float* d = pass == 0 ? c->d_raw : c->d_raw_nrm;
+      const float* h = pass == 0 ? xyz_block : normals_block;
+      if (!d) continue;
+      if (ctx->world > 1 && cudaMemsetAsync(d, 0, words * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+      if (n_block && cudaMemcpyAsync(d + 3 * first_index, h, 3 * n_block * sizeof(float), cudaMemcpyHostToDevice,
+                                     ctx->stream) != cudaSuccess)
+        return fail(CB_ERR_CUDA);
+      if (ctx->world > 1) {
+        const int rc = nccl_allreduce_sum_u32(ctx, reinterpret_cast<uint32_t*>(d), words);
+        if (rc != CB_OK) return fail(rc);
+      }
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+  }
+  *out = c;
+  return CB_OK;
+}
+
 int cb_cloud_create(cb_context* ctx, const float* xyz, const float* normals, size_t n, uint64_t index_offset,
                     cb_cloud** out) {
   return cloud_create_common(ctx, xyz, normals, n, index_offset, cudaMemcpyHostToDevice, out);

@@ -234,6 +234,7 @@ void engine_release_pairs(cb_context* ctx, EnginePairs* pairs);
 int nccl_unique_id(void* out128);
 int nccl_init(cb_context* ctx, const void* id128, int rank, int world);
 int nccl_allreduce_sum_f64(cb_context* ctx, double* d_buf, size_t count);
+int nccl_allreduce_sum_u32(cb_context* ctx, uint32_t* d_buf, size_t count);
 void nccl_destroy(cb_context* ctx);
 
 }  // namespace cb

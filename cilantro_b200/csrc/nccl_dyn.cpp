@@ -25,6 +25,7 @@ typedef int (*fn_comm_destroy)(NcclComm);
 typedef const char* (*fn_get_error_string)(int);
 
 constexpr int kNcclFloat64 = 8;  // ncclDataType_t::ncclFloat64 / ncclDouble
+constexpr int kNcclUint32 = 3;   // ncclDataType_t::ncclUint32
 constexpr int kNcclSum = 0;      // ncclRedOp_t::ncclSum
 
 struct Api {
@@ -110,6 +111,20 @@ int nccl_allreduce_sum_f64(cb_context* ctx, double* d_buf, size_t count) {
     return CB_ERR_NCCL;
   }
   int rc = a->all_reduce(d_buf, d_buf, count, kNcclFloat64, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->stream);
+  if (rc != 0) return fail("ncclAllReduce", rc);
+  return CB_OK;
+}
+
+// Integer sum of 32-bit words: with every word non-zero on at most one rank this is an exact all-gather of bit patterns
+// (used to replicate a cloud whose blocks were uploaded by different ranks: cb_cloud_create_replicated).
+int nccl_allreduce_sum_u32(cb_context* ctx, uint32_t* d_buf, size_t count) {
+  if (ctx->world <= 1) return CB_OK;
+  Api* a = api();
+  if (!a || !ctx->nccl_comm) {
+    set_error("communicator not initialised");
+    return CB_ERR_NCCL;
+  }
+  int rc = a->all_reduce(d_buf, d_buf, count, kNcclUint32, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->stream);
   if (rc != 0) return fail("ncclAllReduce", rc);
   return CB_OK;
 }

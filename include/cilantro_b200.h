@@ -101,6 +101,14 @@ int cb_cloud_create_pair(cb_context* ctx, const float* xyz_a, const float* norma
 /* Same, from packed xyz already in device memory (used when inputs are HBM-resident). */
 int cb_cloud_create_from_device(cb_context* ctx, const float* d_xyz, const float* d_normals, size_t n,
                                 uint64_t index_offset, cb_cloud** out);
+
+/* Multi-rank: a cloud EVERY rank needs in full (the replicated destination cloud of a sharded ICP —
+ * SURVEY 8e) built from its contiguous blocks: each rank uploads only block [first_index, first_index + n_block) of the
+ * n_total points over its own PCIe link, the blocks are exchanged over NVLink (NCCL) and every rank ends up with the
+ * same cloud as cb_cloud_create(whole array) would give it, bit for bit. Collective over the context's communicator
+ * (cb_context_init_comm); with world == 1 it is cb_cloud_create. Normals: present on all ranks or on none. */
+int cb_cloud_create_replicated(cb_context* ctx, const float* xyz_block, const float* normals_block, size_t n_block,
+                               uint64_t first_index, size_t n_total, cb_cloud** out);
 void cb_cloud_destroy(cb_cloud* c);
 size_t cb_cloud_size(const cb_cloud* c);
 /* Grid facts for DESIGN/bench reporting: cell edge, dims[3], occupied-cell mean occupancy. */

@@ -179,3 +179,62 @@ def test_library_carries_only_sm_100a_code():
     for kernel in ("icp_pass_kernel", "kmeans_assign_kernel", "ransac_score_kernel", "moments_kernel",
                    "normals_knn_kernel", "radix_scatter_kernel", "bin_reduce_kernel", "pairs_pass_kernel"):
         assert kernel in syms, kernel
+
+
+def _kabsch_numpy(d, q):
+    """estimateTransformPointToPointMetric (transform_estimation.hpp:12-48) with numpy: R = U V^T of
+    sigma = (d - mu_d)(q - mu_q)^T / n, reflection fixed on the LAST column of U."""
+    mud, muq = d.mean(0), q.mean(0)
+    sigma = (d - mud).T @ (q - muq) / len(d)
+    U, S, Vt = np.linalg.svd(sigma)
+    if np.linalg.det(U) * np.linalg.det(Vt) < 0:
+        U[:, 2] = -U[:, 2]
+    R = U @ Vt
+    return np.hstack([R, (mud - R @ muq)[:, None]])
+
+
+@pytest.mark.parametrize("case", ["generic", "near_identity", "planar", "reflection", "collinear"])
+def test_rotation_solver_polar_and_svd_paths(cb, case):
+    """solve_core.hpp takes the polar (Newton) iteration when det > 0 and the matrix is well conditioned, and the
+    Jacobi SVD otherwise (reflection / rank-deficient rules): both against numpy's SVD, on inputs built to hit each."""
+    rng = np.random.default_rng({"generic": 1, "near_identity": 2, "planar": 3, "reflection": 4, "collinear": 5}[case])
+    worst = 0.0
+    for _ in range(50):
+        n = 60
+        q = rng.normal(size=(n, 3))
+        if case == "planar":
+            q[:, 2] = 0.0  # sigma has a zero singular value: SVD path, u2 = u0 x u1
+        if case == "collinear":
+            q[:, 1:] = 0.0
+        ang = rng.normal(size=3) * (0.01 if case == "near_identity" else 1.0)
+        th = np.linalg.norm(ang)
+        k = ang / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+        d = q @ R.T + rng.normal(size=3)
+        if case == "reflection":
+            d = d * np.array([1.0, 1.0, -1.0]) + 1e-3 * rng.normal(size=(n, 3))  # det(sigma) < 0: Kabsch must still return a rotation
+        s = np.zeros(16)
+        s[0] = n
+        s[1:4] = d.sum(0)
+        s[4:7] = q.sum(0)
+        s[7:16] = (d.T @ q).ravel()
+        T, ok = cb.solve_kabsch_moments(s)
+        assert ok
+        Rg = T[:, :3].astype(np.float64)
+        assert abs(np.linalg.det(Rg) - 1.0) < 1e-5 and np.abs(Rg @ Rg.T - np.eye(3)).max() < 1e-5
+        if case in ("generic", "near_identity", "reflection"):
+            worst = max(worst, np.abs(T - _kabsch_numpy(d, q)).max())
+        else:  # rank-deficient: the rotation is not unique, but it must map the points correctly
+            worst = max(worst, np.abs((q @ Rg.T + T[:, 3]) - d).max())
+    assert worst < 2e-5, worst
+
+
+def test_icp_params_layout_matches_the_header(cb):
+    """capi.IcpParams mirrors struct cb_icp_params field by field (order and count; sizes follow from the types)."""
+    hdr = open(os.path.join(ROOT, "include", "cilantro_b200.h")).read()
+    body = hdr[hdr.index("typedef struct cb_icp_params {"):hdr.index("} cb_icp_params;")]
+    names = re.findall(r"^\s*(?:int32_t|float|double)\s+(\w+)(?:\[\d+\])?;", body, re.M)
+    assert names == [f[0] for f in cb.IcpParams._fields_], (names, [f[0] for f in cb.IcpParams._fields_])
+    p = cb.icp_params(pt_rbf_sigma=0.5, host_loop=True)
+    assert p.host_loop == 1 and p.pt_weight_kind == 1 and abs(p.pt_weight_coeff + 2.0) < 1e-6 and p.pl_weight_kind == 0

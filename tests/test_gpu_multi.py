@@ -31,7 +31,12 @@ def _worker(rank, world, port, out_dir):
     assert cdist.attach_comm(ctx) == (rank, world)
     dst, src, nrm, T_ref = synth.icp_pair(200000, seed=5, noise=0.001, with_normals=True)
     lo, hi = cdist.shard_bounds(src.shape[0], rank, world)
-    d_dst = capi.Cloud(ctx, dst, nrm)
+    # the replicated destination cloud from its blocks (each rank uploads half, NVLink exchange): bit-identical to a
+    # plain upload of the whole cloud
+    dlo, dhi = cdist.shard_bounds(dst.shape[0], rank, world)
+    d_dst = capi.Cloud.replicated(ctx, dst[dlo:dhi], nrm[dlo:dhi], dlo, dst.shape[0])
+    got_p, got_n = d_dst.download(normals=True)
+    assert np.array_equal(got_p.view(np.uint32), dst.view(np.uint32)) and np.array_equal(got_n.view(np.uint32), nrm.view(np.uint32))
     d_src = capi.Cloud(ctx, src[lo:hi], None, index_offset=lo)
     icp = capi.Icp(ctx, d_dst, d_src)
     out = {}
