@@ -12,7 +12,7 @@ reduction (+ all-reduce) + solve) on the named workload.
   N > 1  BASELINE.json configs[2], STRONG-scaled (one process per GPU under torchrun): 10 M destination points +
          normals replicated on every rank, the 10 M source points split into N contiguous shards, combined metric
          (w_pt 0.1, w_pl 1), max_distance^2 = 0.01^2. The only exchange per iteration is the all-reduce of the 28
-         normal-equation values, fused into the iteration kernel's epilogue over NVLink peer memory. `secondary`
+         normal-equation values, done over NVLink peer memory by the iteration's one-warp finish kernel. `secondary`
          carries KMeans3f 50 M x 1024 sharded over the N ranks. (The N = 1 point of this strong-scaling curve is
          `secondary.icp_combined_10m` of the N = 1 line.)
 
@@ -245,8 +245,8 @@ def workload_config(args, name, w, world, scaling, n_src_rank, n_dst):
                      f"noise +-0.001), max_distance^2={w['max_d2']:g}, fixed iteration count (tol=0), {scaling} scaling"),
         "parallelism": (f"src sharded x{world}, dst replicated, one 16-value (p2p) / 28-value all-reduce per iteration, "
                         + ("ncclAllReduce (host loop)" if os.environ.get("CB_NO_FUSED_EXCHANGE") else
-                           "fused into the iteration kernel's epilogue over NVLink peer memory; transform solved on the "
-                           "device, iterations enqueued back to back")),
+                           "exchanged over NVLink peer memory by the iteration's one-warp finish kernel, which also solves "
+                           "the transform on the device; iterations enqueued back to back")),
         "l2": ("NOT flushed (--no-flush experiment; inputs smaller than L2 stay resident)" if getattr(args, "no_flush", False)
                else "flushed before every timed iteration (256 MiB memset outside the CUDA-event bracket)"),
     }
