@@ -87,3 +87,51 @@ def test_two_gpu_sharded_equals_single_gpu(cb, ctx, tmp_path):
     assert (labels != km["labels"]).sum() <= 3
     p = cb.pca(ctx, cb.Cloud(ctx, pts))
     assert np.allclose(r0["pca_cov"], p["cov"], rtol=1e-6, atol=1e-8) and np.array_equal(r0["pca_cov"], r1["pca_cov"])
+
+
+def _worker_dead_peer(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), CB_EXCHANGE_TIMEOUT_MS="400")
+    import time
+
+    from cilantro_b200 import capi, dist as cdist, synth
+
+    cdist.init_process_group(backend="nccl")
+    ctx = capi.Context(rank)
+    assert cdist.attach_comm(ctx) == (rank, world)
+    dst, src, _, _ = synth.icp_pair(50000, seed=6, noise=0.001)
+    lo, hi = cdist.shard_bounds(src.shape[0], rank, world)
+    icp = capi.Icp(ctx, capi.Cloud(ctx, dst), capi.Cloud(ctx, src[lo:hi], None, index_offset=lo))
+    kw = dict(metric="p2p", max_iter=5, tol=0.0, max_d2=np.float32(0.03**2))
+    ok = icp.estimate(**kw)  # both ranks take part: fine
+    status = "ok"
+    t0 = time.perf_counter()
+    if rank == 0:
+        # rank 1 never issues its passes: the in-kernel wait for its row must give up after CB_EXCHANGE_TIMEOUT_MS and
+        # the call must come back with an error instead of hanging (reduce.cuh, exchange_rows)
+        try:
+            icp.estimate(**kw)
+            status = "returned without an error"
+        except capi.CbError as e:
+            status = "error: " + str(e)
+    dt = time.perf_counter() - t0
+    with open(os.path.join(out_dir, f"dead{rank}.txt"), "w") as f:
+        f.write(f"{status}\n{dt}\n{ok['iterations']}\n")
+    import torch.distributed as dist
+
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_dead_peer_times_out_instead_of_hanging(cb, tmp_path):
+    import torch
+    import torch.multiprocessing as mp
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mp.spawn(_worker_dead_peer, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    status, dt, iters = open(tmp_path / "dead0.txt").read().split("\n")[:3]
+    assert int(iters) == 5
+    assert status.startswith("error") and "peer rank" in status, status
+    assert float(dt) < 10.0, dt
