@@ -40,10 +40,23 @@ namespace cb {
 namespace {
 
 constexpr int kBlock = kReduceBlock;
-#ifndef CB_LOOP_QPT
-#define CB_LOOP_QPT 16
+// 256-query chunks per block (tile size / 256) of the search kernel of a warm iteration. The host cannot know how many
+// queries an iteration will have to search again, but the sequence is predictable for a converging run (10^6, 19 %, 7 %,
+// 0.07 %, then a few dozen queries at 1 M): the first kDenseIters warm iteration(s) use small tiles (a tile's first 256
+// flagged queries are searched by the inline body, only the rest by the slower out-of-line copy), later iterations
+// large ones (a tile without flagged queries costs its block ~3 us of latency, so fewer, larger tiles). Either
+// variant is correct for any number of flagged queries. Measured (B200): small tiles for iterations 1-3 made iteration 1
+// 20 % faster and iterations 2-3 up to 50 % slower (mostly empty tiles already); small tiles for iteration 1 only, 8192-query
+// tiles afterwards: 1 M p2p 0.89 -> 0.87 ms per 15 iterations, 10 M combined 5.98 -> 5.7 ms per 10.
+#ifndef CB_LOOP_QPT_DENSE
+#define CB_LOOP_QPT_DENSE 4
 #endif
-constexpr int kQptWarm = CB_LOOP_QPT;  // 256-query chunks per block of the search kernel once the cache is warm
+#ifndef CB_LOOP_QPT
+#define CB_LOOP_QPT 32
+#endif
+constexpr int kQptDense = CB_LOOP_QPT_DENSE;
+constexpr int kQptWarm = CB_LOOP_QPT;
+constexpr int kDenseIters = 1;
 constexpr float kUp18 = 1.0000038146972656f;    // 1 + 2^-18
 constexpr float kDown18 = 0.9999961853027344f;  // 1 - 2^-18
 constexpr float kDown17 = 0.9999923706054688f;  // 1 - 2^-17
@@ -784,6 +797,7 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
   // iterations: cached pass (kWarmTile queries per block) + search kernel over the flagged queries
   const int blocks_cold = std::max(1, (int)((ns + kBlock - 1) / kBlock));
   const int blocks_search = std::max(1, (int)((ns + (size_t)kQptWarm * kBlock - 1) / ((size_t)kQptWarm * kBlock)));
+  const int blocks_dense = std::max(1, (int)((ns + (size_t)kQptDense * kBlock - 1) / ((size_t)kQptDense * kBlock)));
   // persistent cached pass: a whole number of resident blocks per SM (never more blocks than tiles).
   // CB_CACHED_REGS=1 selects the register-staged version (icp_cached_kernel) for A/B measurements.
   static const bool cached_regs = getenv("CB_CACHED_REGS") != nullptr;
@@ -851,7 +865,10 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
             icp_cached_kernel<kModeP2PCentered><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
           else
             CB_CUDA(launch_pdl(icp_cached_pipe_kernel<kModeP2PCentered>, blocks_cached, kBlock, pipe_smem, ctx->stream, a));
-          CB_CUDA(launch_pdl(icp_search_kernel<kModeP2PCentered, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
+          if (issued + k <= kDenseIters)
+            CB_CUDA(launch_pdl(icp_search_kernel<kModeP2PCentered, kQptDense, false>, blocks_dense, kBlock, 0, ctx->stream, a));
+          else
+            CB_CUDA(launch_pdl(icp_search_kernel<kModeP2PCentered, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
         }
       } else {
         if (cold) {
@@ -861,7 +878,10 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
             icp_cached_kernel<kModeCombined><<<blocks_cached, kBlock, 0, ctx->stream>>>(a);
           else
             CB_CUDA(launch_pdl(icp_cached_pipe_kernel<kModeCombined>, blocks_cached, kBlock, pipe_smem, ctx->stream, a));
-          CB_CUDA(launch_pdl(icp_search_kernel<kModeCombined, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
+          if (issued + k <= kDenseIters)
+            CB_CUDA(launch_pdl(icp_search_kernel<kModeCombined, kQptDense, false>, blocks_dense, kBlock, 0, ctx->stream, a));
+          else
+            CB_CUDA(launch_pdl(icp_search_kernel<kModeCombined, kQptWarm, false>, blocks_search, kBlock, 0, ctx->stream, a));
         }
       }
       if (prm->metric == CB_ICP_POINT_TO_POINT)
