@@ -716,19 +716,20 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
     CB_TRY(icp_fill_args(icp, prm, T, nullptr, false, &a));
     if (engine) {
-      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeP2P, false, false));
+      // moments about the pivots (dst mean, T * src mean): no cancellation for clouds far from the origin
+      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeP2PCentered, false, false));
       CB_TRY(icp_fetch(ctx, kP2PValues, sums));
-      kabsch_from_moments(sums, Titer);
+      kabsch_from_pivoted_moments(sums, a.dm, a.sm, Titer);
       *n_corr = sums[0];
       icp->nn_valid = true;
       icp->nn_stored = false;
       return CB_OK;
     }
     if (k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
-    CB_TRY(launch_icp_pass(ctx, a, kModeP2P, true, false, false));
+    CB_TRY(launch_icp_pass(ctx, a, kModeP2PCentered, true, false, false));
     if (k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
     CB_TRY(icp_fetch(ctx, kP2PValues, sums));
-    kabsch_from_moments(sums, Titer);
+    kabsch_from_pivoted_moments(sums, a.dm, a.sm, Titer);
     *n_corr = sums[0];
     icp->nn_valid = true;
     icp->warm_ok = true;

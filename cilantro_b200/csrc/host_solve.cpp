@@ -10,6 +10,9 @@ namespace cb {
 
 void t34_identity(float* T) { sc::t34_identity(T); }
 bool kabsch_from_moments(const double* s, float* T) { return sc::kabsch_from_moments(s, nullptr, nullptr, T); }
+bool kabsch_from_pivoted_moments(const double* s, const float* pd, const float* pq, float* T) {
+  return sc::kabsch_from_moments(s, pd, pq, T);
+}
 bool gauss_newton_update(const double* s28, const float* Tin, float* Tout, float* dtheta_norm) {
   return sc::gauss_newton_update(s28, Tin, Tout, dtheta_norm);
 }

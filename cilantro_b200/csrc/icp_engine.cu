@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kReduceBlock) pairs_pass_kernel(const IcpArgs 
                                                                   const float* __restrict__ src_raw,
                                                                   const float* __restrict__ src_nrm, const bool has_pt,
                                                                   const bool has_pl) {
-  constexpr int NV = (MODE == kModeP2P) ? kP2PValues : kCombinedValues;
+  constexpr int NV = (MODE == kModeP2P || MODE == kModeP2PCentered) ? kP2PValues : kCombinedValues;
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) acc[i] = 0.0;
@@ -224,7 +224,11 @@ int launch_pairs_pass(cb_context* ctx, const IcpArgs& a, const EnginePairs& pair
   args.rs.ex.enabled = 0;
   ctx->pass_armed = false;
   const float* src_nrm = (mode == kModeCombined) ? src->d_raw_nrm : nullptr;
-  if (mode == kModeP2P)
+  if (mode == kModeP2PCentered)
+    pairs_pass_kernel<kModeP2PCentered><<<blocks, kReduceBlock, 0, ctx->stream>>>(args, pairs.first, pairs.second, pairs.d2,
+                                                                                pairs.count, dst->d_raw, dst->d_raw_nrm, src->d_raw,
+                                                                                src_nrm, false, false);
+  else if (mode == kModeP2P)
     pairs_pass_kernel<kModeP2P><<<blocks, kReduceBlock, 0, ctx->stream>>>(args, pairs.first, pairs.second, pairs.d2,
                                                                         pairs.count, dst->d_raw, dst->d_raw_nrm, src->d_raw, src_nrm,
                                                                         false, false);

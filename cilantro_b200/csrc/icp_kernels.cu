@@ -36,7 +36,7 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) 
 
 template <int MODE, bool SEARCH>
 __global__ void __launch_bounds__(kBlock, CB_ICP_MIN_BLOCKS) icp_pass_kernel(const IcpArgs a, const bool has_pt, const bool has_pl) {
-  constexpr int NV = (MODE == kModeP2P) ? kP2PValues : (MODE == kModeCombined ? kCombinedValues : 1);
+  constexpr int NV = (MODE == kModeP2P || MODE == kModeP2PCentered) ? kP2PValues : (MODE == kModeCombined ? kCombinedValues : 1);
   double acc[NV];
 #pragma unroll
   for (int i = 0; i < NV; i++) acc[i] = 0.0;
@@ -215,6 +215,8 @@ int launch_icp_pass(cb_context* ctx, const IcpArgs& a, int mode, bool search, bo
       icp_pass_kernel<kModeP2P, true><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
     else
       icp_pass_kernel<kModeP2P, false><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
+  } else if (mode == kModeP2PCentered) {  // Kabsch moments about the pivots a.dm / a.sm (the ICP loop; always a search pass)
+    icp_pass_kernel<kModeP2PCentered, true><<<blocks, kBlock, 0, ctx->stream>>>(args, false, false);
   } else {
     if (search)
       icp_pass_kernel<kModeCombined, true><<<blocks, kBlock, 0, ctx->stream>>>(args, has_pt, has_pl);

@@ -9,7 +9,7 @@ enum IcpMode : int {
   kModeKnn = 0,       // per-query nearest neighbour only (cb_knn1_radius / correspondences)
   kModeP2P = 1,       // Kabsch moments: n, sum d, sum q, sum d q^T                       (16 values)
   kModeCombined = 2,  // Gauss-Newton normal equations: n, upper AtA (21), Atb (6)         (28 values)
-  kModeP2PCentered = 3,  // Kabsch moments about the pivots (dst mean, T * src mean); device loop only
+  kModeP2PCentered = 3,  // Kabsch moments about the pivots (dst mean, T * src mean): what both ICP loops accumulate
 };
 
 constexpr int kP2PValues = 16;

@@ -62,7 +62,10 @@ def attach_comm(ctx):
     ctx.init_comm(uid, rank, world)
     # fused exchange over NVLink peer memory: all-gather the CUDA-IPC handles, map the peers' tables.
     # All ranks must take the same path, so the outcome is agreed on before anyone proceeds.
-    if os.environ.get("CB_NO_FUSED_EXCHANGE") is None:
+    # every rank must take the same path: if ANY rank was started with CB_NO_FUSED_EXCHANGE, nobody maps the tables and
+    # all ranks reduce through NCCL (a rank waiting in the fused exchange for a peer that went to NCCL would only time out)
+    want_fused = min_over_ranks(0 if os.environ.get("CB_NO_FUSED_EXCHANGE") is not None else 1)
+    if want_fused:
         handles = [None] * world
         dist.all_gather_object(handles, ctx.ipc_handle())
         ok = 1

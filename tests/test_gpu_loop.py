@@ -145,3 +145,25 @@ def test_non_converging_run_is_handed_over_to_the_host_loop(cb, ctx):
     icp2 = cb.Icp(ctx, cb.Cloud(ctx, dst2), cb.Cloud(ctx, src2))
     icp2.estimate(**kw)
     assert icp2.loop_cache()[2] < n // 4
+
+
+def test_clouds_far_from_the_origin(cb, ctx):
+    """Kabsch moments are taken about the pivots (dst mean, T * src mean) in both loops: a cloud 2000 units away from
+    the origin registers as well as the same cloud at the origin (raw second moments would cancel ~1e7 against ~0.1)."""
+    dst, src, _, T_ref = _pair(60000, 13, normals=False)
+    off = np.array([2000.0, -1500.0, 800.0])
+    # x_dst = R x_src + t  ->  (x_dst + off) = R (x_src + off) + (t + off - R off)
+    R, t = np.asarray(T_ref)[:, :3], np.asarray(T_ref)[:, 3]
+    T_far = np.hstack([R, (t + off - R @ off)[:, None]])
+    dst_f, src_f = (dst + off).astype(np.float32), (src + off).astype(np.float32)
+    icp = cb.Icp(ctx, cb.Cloud(ctx, dst_f), cb.Cloud(ctx, src_f))
+    kw = dict(metric="p2p", max_iter=12, tol=0.0, max_d2=np.float32(0.03**2))
+    a = icp.estimate(host_loop=True, **kw)
+    b = icp.estimate(host_loop=False, **kw)
+    assert a["num_corr"] == b["num_corr"] and np.abs(a["T"][:, :3] - b["T"][:, :3]).max() < 1e-6
+    # rotation recovered as well as the same pair registers at the origin (noise 0.002, 60 k points: ~1e-5), given the
+    # fp32 coordinate spacing of 1.2e-4 at |x| ~ 2000
+    o = cb.Icp(ctx, cb.Cloud(ctx, dst), cb.Cloud(ctx, src)).estimate(**kw)
+    err_far, err_origin = np.abs(b["T"][:, :3] - R).max(), np.abs(o["T"][:, :3] - R).max()
+    assert err_far < max(1e-4, 3 * err_origin), (err_far, err_origin)
+    assert np.abs(b["T"][:, 3] - T_far[:, 3]).max() < 0.3
