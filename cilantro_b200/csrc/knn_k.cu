@@ -1,5 +1,6 @@
 // General-k nearest neighbours over the grid (product code, sm_100a).
-// Replaces the batched KDTree::kNNInRadiusSearch / kNNSearch (core/kd_tree.hpp:215-318) for k <= 32:
+// Replaces the batched KDTree::kNNInRadiusSearch / kNNSearch (core/kd_tree.hpp:215-318) for k <= 256 (the k-best list is a
+// per-thread array: registers for small k, L1-resident local memory for large k; the reference is unbounded in k):
 // same shell sweep as nn_search.cuh, with a per-thread sorted list of the k best (d2, index) pairs
 // whose worst entry plays the role of nanoflann's worstDist() (kd_tree.hpp:101).
 #include "cb_internal.hpp"
@@ -11,7 +12,7 @@ using namespace cb;
 
 namespace {
 
-constexpr int kMaxK = 32;
+constexpr int kMaxK = 256;
 constexpr int kBlock = 128;
 
 struct KBest {
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kBlock) knn_k_kernel(const GridView g, const f
 extern "C" int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, int k,
                              float max_d2, int64_t* idx, float* d2, uint32_t* counts) {
   CB_CHECK(ctx && ref && qry && idx && d2, CB_ERR_INVALID, "null argument");
-  CB_CHECK(k >= 1 && k <= kMaxK, CB_ERR_UNSUPPORTED, "k must be in [1, 32]");
+  CB_CHECK(k >= 1 && k <= kMaxK, CB_ERR_UNSUPPORTED, "k must be in [1, 256]");
   CB_CHECK(ref->ctx == ctx && qry->ctx == ctx, CB_ERR_INVALID, "cloud belongs to another context");
   CB_CUDA(cudaSetDevice(ctx->device));
   CB_TRY(ensure_index(const_cast<cb_cloud*>(ref)));
@@ -97,8 +98,14 @@ extern "C" int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_clou
     knn_k_kernel<4><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
   else if (k <= 16)
     knn_k_kernel<16><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
-  else
+  else if (k <= 32)
     knn_k_kernel<32><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
+  else if (k <= 64)
+    knn_k_kernel<64><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
+  else if (k <= 128)
+    knn_k_kernel<128><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
+  else
+    knn_k_kernel<256><<<blocks, kBlock, 0, ctx->stream>>>(g, qry->d_pts, (uint32_t)nq, T, k, max_d2, d_idx, d_d2, d_cnt);
   ctx->launches += 1;
   CB_CUDA(cudaGetLastError());
   std::vector<int> h_idx(nq * k);

@@ -22,7 +22,7 @@ using namespace cb;
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kMaxK = 32;
+constexpr int kMaxK = 128;  // k-best lists in shared memory: 8 B x k x 128 threads (dynamic above 48 KB)
 
 // Cyclic Jacobi on a symmetric 3x3 (a = xx,xy,xz,yy,yz,zz). Eigenvalues ascending in w, v0 = unit
 // eigenvector of w[0]. The matrix is scaled by its largest |entry| first, like
@@ -135,8 +135,9 @@ __device__ __forceinline__ void finish_point(const NormalOut& o, uint32_t qi, in
 
 template <int K>
 __global__ void __launch_bounds__(kBlock) normals_knn_kernel(const GridView g, int k, float max_d2, const NormalOut o) {
-  __shared__ float sd[K][kBlock];
-  __shared__ uint32_t sp[K][kBlock];
+  extern __shared__ __align__(16) unsigned char knn_smem[];
+  float(*sd)[kBlock] = reinterpret_cast<float(*)[kBlock]>(knn_smem);
+  uint32_t(*sp)[kBlock] = reinterpret_cast<uint32_t(*)[kBlock]>(knn_smem + sizeof(float) * K * kBlock);
   const int t = threadIdx.x;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t qi = blockIdx.x * blockDim.x + t; qi < g.n; qi += stride) {
@@ -282,7 +283,7 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
                                          float* curvature, float* cov6, float* gpu_ms) {
   CB_CHECK(ctx && cloud, CB_ERR_INVALID, "null argument");
   CB_CHECK(cloud->ctx == ctx, CB_ERR_INVALID, "cloud belongs to another context");
-  CB_CHECK(k >= 0 && k <= kMaxK, CB_ERR_UNSUPPORTED, "k must be in [0, 32] (0 = radius neighbourhood)");
+  CB_CHECK(k >= 0 && k <= kMaxK, CB_ERR_UNSUPPORTED, "k must be in [0, 128] (0 = radius neighbourhood)");
   CB_CHECK(k > 0 || radius2 > 0.f, CB_ERR_INVALID, "need k > 0 and/or radius2 > 0");
   CB_CUDA(cudaSetDevice(ctx->device));
   if (gpu_ms) *gpu_ms = 0.f;
@@ -318,11 +319,22 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
   if (k == 0)
     normals_radius_kernel<<<blocks, kBlock, 0, ctx->stream>>>(g, max_d2, o);
   else if (k <= 8)
-    normals_knn_kernel<8><<<blocks, kBlock, 0, ctx->stream>>>(g, k, max_d2, o);
+    normals_knn_kernel<8><<<blocks, kBlock, 8 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
   else if (k <= 16)
-    normals_knn_kernel<16><<<blocks, kBlock, 0, ctx->stream>>>(g, k, max_d2, o);
-  else
-    normals_knn_kernel<32><<<blocks, kBlock, 0, ctx->stream>>>(g, k, max_d2, o);
+    normals_knn_kernel<16><<<blocks, kBlock, 16 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
+  else if (k <= 32)
+    normals_knn_kernel<32><<<blocks, kBlock, 32 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
+  else if (k <= 64) {
+    static const cudaError_t attr = cudaFuncSetAttribute(normals_knn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         64 * kBlock * 8);
+    CB_CUDA(attr);
+    normals_knn_kernel<64><<<blocks, kBlock, 64 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
+  } else {
+    static const cudaError_t attr = cudaFuncSetAttribute(normals_knn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         128 * kBlock * 8);
+    CB_CUDA(attr);
+    normals_knn_kernel<128><<<blocks, kBlock, 128 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
+  }
   ctx->launches += 1;
   if (gpu_ms) CB_CUDA(cudaEventRecord(ev.e1, ctx->stream));
   CB_CUDA(cudaGetLastError());

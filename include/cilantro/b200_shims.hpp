@@ -335,7 +335,7 @@ public:
     const size_t nq = queries.cols();
     NeighborhoodSetResult out(nq);
     if (nq == 0 || k == 0 || n_ == 0) return out;
-    if (k > 32) throw std::runtime_error("cilantro_b200: kNN supports k <= 32");
+    if (k > 256) throw std::runtime_error("cilantro_b200: kNN supports k <= 256");
     std::vector<int64_t> idx(nq * k);
     std::vector<float> d2(nq * k);
     std::vector<uint32_t> cnt(nq);
@@ -977,7 +977,7 @@ public:
 
 private:
   const NormalEstimation3f& run(VectorSet3f* normals, std::vector<float>* curvature, size_t k, float radius) const {
-    if (k > 32) throw std::runtime_error("cilantro_b200: normal estimation supports k <= 32 neighbours");
+    if (k > 128) throw std::runtime_error("cilantro_b200: normal estimation supports k <= 128 neighbours");
     if (normals) normals->resize(3, n_);
     if (curvature) curvature->resize(n_);
     if (n_ == 0) return *this;

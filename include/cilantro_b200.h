@@ -124,7 +124,7 @@ int cb_cloud_grid_info(const cb_cloud* c, float* cell_edge, int* dims3, double* 
  * max_d2 = FLT_MAX gives KDTree::nearestNeighborSearch (core/kd_tree.hpp:181-204). */
 int cb_knn1_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, float max_d2,
                    int64_t* idx, float* d2);
-/* General k (1..32): KDTree::kNNInRadiusSearch / kNNSearch batched (core/kd_tree.hpp:215-318).
+/* General k (1..256; CB_ERR_UNSUPPORTED above): KDTree::kNNInRadiusSearch / kNNSearch batched (core/kd_tree.hpp:215-318).
  * idx/d2 are n_qry x k, ascending d2, unused slots idx = -1. counts (may be NULL) = found per query. */
 int cb_knn_radius(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, const float* T12, int k,
                   float max_d2, int64_t* idx, float* d2, uint32_t* counts);
@@ -146,7 +146,8 @@ int cb_radius_search(cb_context* ctx, const cb_cloud* ref, const cb_cloud* qry, 
  * orients by those instead (setReferenceNormals, :63-69, :351-355; takes precedence, :281-291). The normals are stored in the cloud on the device (as
  * PointCloud::normals is filled), so a combined-metric ICP can follow without a host round trip.
  * Host outputs (each may be NULL): normals 3n, curvature n, cov6 6n (xx,xy,xz,yy,yz,zz of the
- * neighbourhood covariance, diagnostic). gpu_ms (may be NULL) = device time of the kernel. k <= 32. */
+ * neighbourhood covariance, diagnostic). gpu_ms (may be NULL) = device time of the kernel. k <= 128
+ * (the k-best lists live in shared memory; CB_ERR_UNSUPPORTED above). */
 int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k, float radius2, const float* view_point3,
                               int use_current_as_ref, float* normals, float* curvature, float* cov6, float* gpu_ms);
 /* ---- voxel-grid downsampling -------------------------------------------------------------------

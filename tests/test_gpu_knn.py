@@ -126,7 +126,7 @@ def test_knn_k_matches_numpy(cb, ctx):
     dst = rng.random((4000, 3), dtype=np.float32)
     qry = rng.random((300, 3), dtype=np.float32)
     ref, q = cb.Cloud(ctx, dst), cb.Cloud(ctx, qry)
-    for k, r2 in ((2, FMAX), (8, 0.08**2), (20, FMAX)):
+    for k, r2 in ((2, FMAX), (8, 0.08**2), (20, FMAX), (50, FMAX), (100, 0.3**2), (200, FMAX), (256, FMAX)):
         idx, d2, cnt = cb.knn_radius(ctx, ref, q, k, None, r2)
         # numpy restatement with the same fp32 arithmetic order
         dx = qry[:, None, 0] - dst[None, :, 0]

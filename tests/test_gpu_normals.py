@@ -19,14 +19,21 @@ def _full(c6):
     return np.stack([c6[:, [0, 1, 2]], c6[:, [1, 3, 4]], c6[:, [2, 4, 5]]], axis=1).astype(np.float64)
 
 
-def _compare(orc, got, ref_out, pts, view_point, cov_exact=True):
+def _compare(orc, got, ref_out, pts, view_point, cov_exact=True, exact_share=1.0):
     n_ref, curv_ref, cov_ref, cnt = ref_out
     nan_ref = np.isnan(n_ref).any(axis=1)
     assert np.array_equal(np.isnan(got["normals"]).any(axis=1), nan_ref)
     assert np.array_equal(np.isnan(got["curvature"]), nan_ref)
     ok = ~nan_ref
-    if cov_exact:
+    if cov_exact and exact_share >= 1.0:
         assert np.array_equal(got["cov6"][ok].view(np.uint32), cov_ref[ok].view(np.uint32)), "covariance not bit-exact"
+    elif cov_exact:
+        # large neighbourhoods: two neighbours at a bit-equal distance are ordered by nanoflann's traversal in the
+        # reference and by index here, which permutes two terms of the fp32 sums of that point
+        same = np.all(got["cov6"][ok].view(np.uint32) == cov_ref[ok].view(np.uint32), axis=1)
+        assert same.mean() >= exact_share, same.mean()
+        scale = np.abs(cov_ref[ok]).max(axis=1, keepdims=True)
+        assert np.all(np.abs(got["cov6"][ok] - cov_ref[ok]) <= 2e-6 * scale)
     else:
         scale = np.abs(cov_ref[ok]).max(axis=1, keepdims=True)
         assert np.all(np.abs(got["cov6"][ok] - cov_ref[ok]) <= 2e-5 * scale)
@@ -47,14 +54,15 @@ def _compare(orc, got, ref_out, pts, view_point, cov_exact=True):
     assert np.allclose(got["curvature"][ok], curv_ref[ok], atol=1e-4)
 
 
-@pytest.mark.parametrize("k", [3, 8, 9, 16, 17, 32])
+@pytest.mark.parametrize("k", [3, 8, 9, 16, 17, 32, 33, 64, 100, 128])
 def test_normals_knn_random_cloud(cb, ctx, orc, k):
     rng = np.random.default_rng(k)
     pts = rng.random((20000, 3), dtype=np.float32)
     vp = [0.5, 0.5, 4.0]
     cloud = cb.Cloud(ctx, pts)
     got = cloud.estimate_normals(k=k, view_point=vp, want_cov=True)
-    _compare(orc, got, orc.estimate_normals(pts, orc.make_knn(pts), k=k, view_point=vp), pts, vp)
+    _compare(orc, got, orc.estimate_normals(pts, orc.make_knn(pts), k=k, view_point=vp), pts, vp,
+             exact_share=1.0 if k <= 32 else 0.95)
 
 
 def test_normals_surface_knn_and_analytic(cb, ctx, orc):
