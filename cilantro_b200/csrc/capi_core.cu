@@ -653,6 +653,7 @@ void cb_icp_destroy(cb_icp* icp) {
   engine_release_pairs(icp->ctx, &icp->pairs);
   if (icp->d_state) cudaFree(icp->d_state);
   if (icp->d_miss_mask) cudaFree(icp->d_miss_mask);
+  if (icp->src_full) cb_cloud_destroy(icp->src_full);
   if (icp->h_state) cudaFreeHost(icp->h_state);
   for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
   delete icp;
@@ -693,13 +694,63 @@ static int icp_fill_args(cb_icp* icp, const cb_icp_params* prm, const float* T, 
 
 // Totals of the last reduction pass: through the fused exchange when the pass carried it (no stream
 // synchronisation: the host polls its mailbox), else all-reduce (NCCL) + copy + synchronise.
-static int icp_fetch(cb_context* ctx, int count, double* out) {
+static int icp_fetch(cb_context* ctx, int count, double* out, bool allreduce = true) {
   if (ctx->pass_armed) return wait_exchange(ctx, count, out);
-  return fetch_result(ctx, count, true, out);
+  return fetch_result(ctx, count, allreduce, out);
 }
+
+// Non-default correspondence-engine modes with several ranks. Their filters rank ALL pairs globally (closest
+// fraction, closest pair per destination point) and FIRST_TO_SECOND searches among ALL transformed source points, so a
+// shard cannot decide anything alone. Every rank therefore holds the whole source cloud (its blocks all-gathered once
+// over NVLink: exact integer-sum all-reduce, as cb_cloud_create_replicated) and runs the same single-GPU list pipeline
+// on it: identical lists, sums and transforms on every rank, no all-reduce per iteration - correct and rank-consistent,
+// not faster than one GPU. The shards must have been created with index_offset = their first global index.
+static int ensure_src_full(cb_icp* icp) {
+  cb_context* ctx = icp->ctx;
+  if (ctx->world <= 1 || icp->src_full) return CB_OK;
+  const cb_cloud* src = icp->src;
+  // total size and normals presence over all ranks
+  double h[2] = {(double)src->n, src->d_raw_nrm ? 1.0 : 0.0};
+  CB_CUDA(cudaMemcpyAsync(ctx->d_result, h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  double tot[2];
+  CB_TRY(fetch_result(ctx, 2, true, tot));
+  const size_t n_total = (size_t)(tot[0] + 0.5);
+  CB_CHECK(src->index_offset + src->n <= n_total, CB_ERR_INVALID,
+           "engine modes across ranks: the source shards need index_offset = their first global index");
+  const bool nrm = tot[1] > 0.5;
+  CB_CHECK(!nrm || (int)(tot[1] + 0.5) == ctx->world, CB_ERR_INVALID, "source normals on some ranks only");
+  cb_cloud* c = new cb_cloud;
+  c->ctx = ctx;
+  c->n = n_total;
+  c->index_offset = 0;
+  const size_t words = 3 * n_total;
+  auto fail = [&](int rc) {
+    cb_cloud_destroy(c);
+    return rc;
+  };
+  for (int pass = 0; pass < (nrm ? 2 : 1); ++pass) {
+    float** d = pass == 0 ? &c->d_raw : &c->d_raw_nrm;
+    const float* mine = pass == 0 ? src->d_raw : src->d_raw_nrm;
+    if (cudaMallocAsync(d, std::max<size_t>(words, 1) * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+    if (cudaMemsetAsync(*d, 0, words * sizeof(float), ctx->stream) != cudaSuccess) return fail(CB_ERR_CUDA);
+    if (src->n && cudaMemcpyAsync(*d + 3 * src->index_offset, mine, 3 * src->n * sizeof(float), cudaMemcpyDeviceToDevice,
+                                  ctx->stream) != cudaSuccess)
+      return fail(CB_ERR_CUDA);
+    const int rc = nccl_allreduce_sum_u32(ctx, reinterpret_cast<uint32_t*>(*d), words);
+    if (rc != CB_OK) return fail(rc);
+  }
+  const int rc = ensure_index(c);
+  if (rc != CB_OK) return fail(rc);
+  icp->src_full = c;
+  return CB_OK;
+}
+
+// the source cloud the engine modes work on: the whole cloud (replicated) with several ranks, else the caller's
+static const cb_cloud* esrc(const cb_icp* icp) { return (icp->ctx->world > 1 && icp->src_full) ? icp->src_full : icp->src; }
 
 // One estimator call of updateEstimate(): returns tform_iter (already un-centred), and the
 // correspondence count of the search pass. k0/k1 (nullable) are recorded around the search kernel.
+
 static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, float* Titer, double* n_corr,
                       cudaEvent_t k0, cudaEvent_t k1) {
   cb_context* ctx = icp->ctx;
@@ -710,15 +761,16 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
   if (engine) {
     // updateCorrespondences(): the explicit list (icp_engine.cu); the passes below accumulate over it
     if (k0) CB_CUDA(cudaEventRecord(k0, ctx->stream));
-    CB_TRY(engine_find_pairs(ctx, icp->dst, icp->src, prm, T, &icp->pairs));
+    CB_TRY(ensure_src_full(icp));
+    CB_TRY(engine_find_pairs(ctx, icp->dst, esrc(icp), prm, T, &icp->pairs));
     if (k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
   }
   if (prm->metric == CB_ICP_POINT_TO_POINT) {
     CB_TRY(icp_fill_args(icp, prm, T, nullptr, false, &a));
     if (engine) {
       // moments about the pivots (dst mean, T * src mean): no cancellation for clouds far from the origin
-      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeP2PCentered, false, false));
-      CB_TRY(icp_fetch(ctx, kP2PValues, sums));
+      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, esrc(icp), kModeP2PCentered, false, false));
+      CB_TRY(icp_fetch(ctx, kP2PValues, sums, /*allreduce=*/false));  // every rank accumulated the whole list
       kabsch_from_pivoted_moments(sums, a.dm, a.sm, Titer);
       *n_corr = sums[0];
       icp->nn_valid = true;
@@ -748,7 +800,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
     CB_TRY(icp_fill_args(icp, prm, T, Tin, max_opt > 1 && !engine, &a));  // (stores d2 too: the RBF weights of inner passes read it)
     const bool search = (it == 0);
     if (engine) {
-      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, icp->src, kModeCombined, w_pt_on,
+      CB_TRY(launch_pairs_pass(ctx, a, icp->pairs, icp->dst, esrc(icp), kModeCombined, w_pt_on,
                                w_pl_on && dst_has_normals));
     } else {
       // the first pass always runs (it is also the correspondence search of this ICP iteration)
@@ -756,7 +808,7 @@ static int icp_update(cb_icp* icp, const cb_icp_params* prm, const float* T, flo
       CB_TRY(launch_icp_pass(ctx, a, kModeCombined, search, w_pt_on, w_pl_on && dst_has_normals));
       if (search && k1) CB_CUDA(cudaEventRecord(k1, ctx->stream));
     }
-    CB_TRY(icp_fetch(ctx, kCombinedValues, sums));
+    CB_TRY(icp_fetch(ctx, kCombinedValues, sums, /*allreduce=*/!(engine && ctx->world > 1)));
     if (search) {
       *n_corr = sums[0];
       icp->nn_valid = true;
@@ -939,7 +991,7 @@ int cb_icp_correspondences(cb_icp* icp, uint64_t* index_first, uint64_t* index_s
     CB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (size_t k = 0; k < m; k++) {
       if (index_first) index_first[k] = (uint64_t)f[k] + icp->dst->index_offset;
-      if (index_second) index_second[k] = (uint64_t)s[k] + icp->src->index_offset;
+      if (index_second) index_second[k] = (uint64_t)s[k] + esrc(icp)->index_offset;  // (several ranks: the global list)
     }
     *count = m;
     return CB_OK;

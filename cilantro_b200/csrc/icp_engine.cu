@@ -250,8 +250,7 @@ void engine_release_pairs(cb_context* ctx, EnginePairs* pairs) {
 
 int engine_find_pairs(cb_context* ctx, const cb_cloud* dst, const cb_cloud* src, const cb_icp_params* prm,
                       const float* T12, EnginePairs* pairs) {
-  CB_CHECK(ctx->world <= 1, CB_ERR_UNSUPPORTED,
-           "non-default correspondence-engine modes are single-GPU (their filters are global over all pairs)");
+  // (with several ranks the caller passes the whole source cloud, replicated: capi_core.cu, ensure_src_full)
   CB_CHECK(prm->search_dir >= CB_SECOND_TO_FIRST && prm->search_dir <= CB_BOTH, CB_ERR_INVALID, "bad search_dir");
   engine_release_pairs(ctx, pairs);
   const uint32_t n_src = (uint32_t)src->n, n_dst = (uint32_t)dst->n;

@@ -56,6 +56,7 @@ struct cb_icp {
   cb::LoopState* d_state = nullptr;
   cb::LoopState* h_state = nullptr;  // pinned
   uint32_t* d_miss_mask = nullptr;   // cached pass -> search kernel: one bit per sorted query
+  cb_cloud* src_full = nullptr;      // world > 1, engine modes: the whole source cloud replicated on this rank (owned)
   bool loop_last = false;            // the last estimate() ran on the device loop
   uint64_t searched_last = 0;        // queries its last iteration searched again (CB_LOOP_TRACE / cb_icp_loop_cache)
 };

@@ -213,7 +213,9 @@ typedef struct cb_icp_params {
   /* Correspondence-engine options (correspondence_search_kd_tree.hpp:46-50, :60-98 setters). The defaults
    * (SECOND_TO_FIRST, fraction 1, no reciprocity, not one-to-one) take the fused single-kernel path; any other
    * setting materialises the correspondence list on the device (search(es) -> union / intersection -> fraction
-   * filter -> one-to-one filter, core/correspondence.hpp:57-100) and accumulates over it. Single GPU only. */
+   * filter -> one-to-one filter, core/correspondence.hpp:57-100) and accumulates over it. With several ranks every rank runs
+   * them on the whole source cloud (shards all-gathered once; create the shards with index_offset = their first global index):
+   * same lists and transforms as one GPU, on every rank. */
   int32_t search_dir;          /* cb_search_dir; default CB_SECOND_TO_FIRST */
   int32_t require_reciprocal;  /* with CB_BOTH: intersection instead of union (:68-70 of ..._utilities.hpp) */
   int32_t one_to_one;          /* keep, per dst (SECOND_TO_FIRST) / src (FIRST_TO_SECOND) point, the closest pair */

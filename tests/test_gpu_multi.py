@@ -44,6 +44,14 @@ def _worker(rank, world, port, out_dir):
         r = icp.estimate(max_iter=8, tol=0.0, max_d2=np.float32(0.03**2), **kw)
         out[name + "_T"] = r["T"]
         out[name + "_n"] = np.array([r["num_corr"]])
+    # non-default correspondence-engine modes with sharded source points: every rank works on the replicated cloud
+    for name, kw in (("eng_frac", dict(metric="p2p", inlier_fraction=0.8, one_to_one=True)),
+                     ("eng_both", dict(metric="combined", w_pt=0.1, w_pl=1.0, search_dir="both", require_reciprocal=True))):
+        r = icp.estimate(max_iter=4, tol=0.0, max_d2=np.float32(0.03**2), **kw)
+        f, s2, v = icp.correspondences()
+        out[name + "_T"] = r["T"]
+        out[name + "_n"] = np.array([r["num_corr"]])
+        out[name + "_f"], out[name + "_s"], out[name + "_v"] = f, s2, v
     # k-means: points sharded, one all-reduce of K x 4 sums per iteration
     pts, cent0 = synth.kmeans_data(300000, 64, seed=3)
     plo, phi = cdist.shard_bounds(pts.shape[0], rank, world)
@@ -79,6 +87,14 @@ def test_two_gpu_sharded_equals_single_gpu(cb, ctx, tmp_path):
         assert np.array_equal(r0[name + "_T"], r1[name + "_T"]), "ranks must agree bit for bit"
         assert r0[name + "_n"][0] == single["num_corr"]
         assert np.abs(r0[name + "_T"] - single["T"]).max() < 2e-7
+    for name, kw in (("eng_frac", dict(metric="p2p", inlier_fraction=0.8, one_to_one=True)),
+                     ("eng_both", dict(metric="combined", w_pt=0.1, w_pl=1.0, search_dir="both", require_reciprocal=True))):
+        single = icp.estimate(max_iter=4, tol=0.0, max_d2=np.float32(0.03**2), **kw)
+        f, s2, v = icp.correspondences()
+        for r in (r0, r1):  # both ranks hold the global list of the single-GPU run, and its transform bit for bit
+            assert np.array_equal(r[name + "_T"], single["T"]) and r[name + "_n"][0] == single["num_corr"]
+            assert np.array_equal(r[name + "_f"], f) and np.array_equal(r[name + "_s"], s2)
+            assert np.array_equal(r[name + "_v"].view(np.uint32), v.view(np.uint32))
     pts, cent0 = synth.kmeans_data(300000, 64, seed=3)
     km = cb.kmeans_cluster(ctx, cb.Cloud(ctx, pts), cent0, max_iter=6, tol=0.0)
     assert np.array_equal(r0["km_cent"], r1["km_cent"])
