@@ -176,9 +176,17 @@ def test_library_carries_only_sm_100a_code():
             if ln.startswith("ELF file")]
     assert elfs and all(".sm_100a.cubin" in ln for ln in elfs), elfs
     syms = subprocess.run(["cuobjdump", "-symbols", lib], capture_output=True, text=True).stdout
-    for kernel in ("icp_pass_kernel", "kmeans_assign_kernel", "ransac_score_kernel", "moments_kernel",
-                   "normals_knn_kernel", "radix_scatter_kernel", "bin_reduce_kernel", "pairs_pass_kernel"):
+    for kernel in ("icp_pass_kernel", "icp_search_kernel", "icp_cached_pipe_kernel", "icp_finish_kernel",
+                   "kmeans_assign_kernel", "ransac_score_kernel", "moments_kernel", "normals_knn_kernel",
+                   "radix_scatter_kernel", "bin_reduce_kernel", "pairs_pass_kernel"):
         assert kernel in syms, kernel
+    # the asynchronous-copy pipeline of the cached pass and the programmatic dependent launch of the loop kernels made
+    # it into the SASS (cp.async -> LDGSTS / LDGDEPBAR, griddepcontrol.wait / launch_dependents -> ACQBULK / PREEXIT)
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "icp_cached_pipe_kernel", lib], capture_output=True, text=True).stdout
+    if "LDGSTS" not in sass:  # older cuobjdump: no demangled -fun match, fall back to the whole library
+        sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    for mnemonic in ("LDGSTS", "LDGDEPBAR", "ACQBULK", "PREEXIT"):
+        assert mnemonic in sass, mnemonic
 
 
 def _kabsch_numpy(d, q):
