@@ -655,6 +655,9 @@ void cb_icp_destroy(cb_icp* icp) {
   if (icp->d_miss_mask) cudaFree(icp->d_miss_mask);
   if (icp->src_full) cb_cloud_destroy(icp->src_full);
   if (icp->h_state) cudaFreeHost(icp->h_state);
+  if (icp->h_state2) cudaFreeHost(icp->h_state2);
+  for (cudaEvent_t e : icp->batch_ev)
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : icp->events) cudaEventDestroy(e);
   delete icp;
 }

@@ -849,10 +849,17 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
   // (the exclusion cache costs more than it saves there). CB_LOOP_NO_HANDOVER=1 keeps the device loop regardless.
   static const bool no_handover = getenv("CB_LOOP_NO_HANDOVER") != nullptr;
   constexpr int kFirstBatch = 4;
+  constexpr int kBridgeBatch = 2;  // enqueued behind the first batch: covers the host's look at the first batch's state
   constexpr double kGiveUpShare = 0.15;
-  bool finished = (max_iter == 0);
-  while (!finished) {
-    const int n = std::min(issued == 0 ? kFirstBatch : kBatch, max_iter - issued);
+  // Batches are enqueued ONE AHEAD of the batch whose state the host is looking at: the device never waits for the host
+  // between batches (with several ranks such a gap showed up as a 1.8 ms peer wait in the next iteration), and the
+  // hand-over / convergence decisions lag by at most one batch. Two pinned copies of LoopState alternate.
+  if (!icp->h_state2) CB_CUDA(cudaMallocHost(&icp->h_state2, sizeof(LoopState)));
+  for (int e = 0; e < 2; ++e)
+    if (!icp->batch_ev[e]) CB_CUDA(cudaEventCreateWithFlags(&icp->batch_ev[e], cudaEventDisableTiming));
+  LoopState* hbuf[2] = {icp->h_state, icp->h_state2};
+  int enq = 0, checked = 0;  // batches enqueued / examined
+  auto enqueue_batch = [&](int n) -> int {
     for (int k = 0; k < n; ++k) {
       if (prm->flush_l2) CB_TRY(cb_context_flush_l2(ctx));
       if (timing) CB_CUDA(cudaEventRecord(icp->events[2 * (issued + k)], ctx->stream));
@@ -894,14 +901,29 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
     }
     CB_CUDA(cudaGetLastError());
     issued += n;
-    CB_CUDA(cudaMemcpyAsync(hs, icp->d_state, sizeof(*hs), cudaMemcpyDeviceToHost, ctx->stream));
-    CB_CUDA(cudaStreamSynchronize(ctx->stream));
-    finished = hs->done != 0 || issued >= max_iter;
-    if (!finished && !no_handover && hs->iters >= kFirstBatch && hs->searched_all > kGiveUpShare * hs->queries_all) {
-      *hand_over = 1;
-      finished = true;
+    CB_CUDA(cudaMemcpyAsync(hbuf[enq & 1], icp->d_state, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream));
+    CB_CUDA(cudaEventRecord(icp->batch_ev[enq & 1], ctx->stream));
+    ++enq;
+    return CB_OK;
+  };
+  bool stop = false, give_up = false;
+  if (max_iter > 0) CB_TRY(enqueue_batch(std::min(kFirstBatch, max_iter)));
+  while (checked < enq) {
+    // (a short bridge batch until the first state has been examined: a run that is given up then costs two more device
+    // iterations, not a full batch)
+    if (!stop && issued < max_iter && enq - checked < 2)
+      CB_TRY(enqueue_batch(std::min(checked == 0 ? kBridgeBatch : kBatch, max_iter - issued)));
+    CB_CUDA(cudaEventSynchronize(icp->batch_ev[checked & 1]));
+    hs = hbuf[checked & 1];
+    ++checked;
+    if (hs->done != 0 || issued >= max_iter) {
+      stop = true;  // converged / failed (launches already enqueued return at once) or everything is enqueued
+    } else if (!no_handover && hs->iters >= kFirstBatch && hs->searched_all > kGiveUpShare * hs->queries_all) {
+      stop = true;  // not converging: no further batch; the one already in flight (if any) still completes
+      give_up = true;
     }
   }
+  if (give_up && hs->done == 0 && hs->iters < max_iter) *hand_over = 1;
   if (max_iter == 0) CB_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->seq = hs->xseq;
   if (hs->done == 2) {

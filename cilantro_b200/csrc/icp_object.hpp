@@ -55,6 +55,8 @@ struct cb_icp {
   // device-resident loop (icp_loop.cu); the per-query cache lives in d_nn_pos (match) / d_nn_d2 (exclusion radius)
   cb::LoopState* d_state = nullptr;
   cb::LoopState* h_state = nullptr;  // pinned
+  cb::LoopState* h_state2 = nullptr; // pinned: the batches' states alternate between the two
+  cudaEvent_t batch_ev[2] = {nullptr, nullptr};  // end of a batch + its state copy
   uint32_t* d_miss_mask = nullptr;   // cached pass -> search kernel: one bit per sorted query
   cb_cloud* src_full = nullptr;      // world > 1, engine modes: the whole source cloud replicated on this rank (owned)
   bool loop_last = false;            // the last estimate() ran on the device loop
