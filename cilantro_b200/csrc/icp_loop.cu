@@ -456,11 +456,12 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeCombined) ? 3 : 4) icp_c
   // (No pdl_launch_dependents() here: released early, the search kernel's blocks were handed to whichever SMs finished
   // their share of this pass first - a few SMs ended up with all of its tiles, and iterations that still search many
   // queries ran 25 % slower.)
-  // The streamed arrays were last written by the PREVIOUS iteration's cached / search kernels, which completed before
-  // the finish kernel this launch depends on even started: they may be requested before the dependency wait.
+  // The dependency wait comes BEFORE the first copies: the cache arrays are rewritten every iteration, their 4-byte
+  // copies go through L1 (cp.async.ca), and only accesses after griddepcontrol.wait are guaranteed to see the previous
+  // kernels' writes. What programmatic launch still buys here: the blocks are resident when the finish kernel ends.
+  pdl_wait();
   stage_a(t0, 0);           // group: A(0)
   stage_a(t0 + stride, 1);  // group: A(1)
-  pdl_wait();               // LoopState (written by the previous iteration's finish kernel)
   if (tid == 0) {
     rsm.arrived = 0u;
     load_block_ctx(a, cx);

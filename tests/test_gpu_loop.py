@@ -17,14 +17,17 @@ def _pair(n, seed, normals=True):
     return synth.icp_pair(n, seed=seed, noise=0.002, with_normals=normals)
 
 
+@pytest.mark.parametrize("timing", [1, 0])
 @pytest.mark.parametrize("metric,kw", [("p2p", {}), ("combined", dict(w_pt=0.1, w_pl=1.0)), ("combined", dict(w_pt=0.0, w_pl=1.0))])
-def test_device_loop_matches_host_loop_every_iteration(cb, ctx, metric, kw):
+def test_device_loop_matches_host_loop_every_iteration(cb, ctx, metric, kw, timing):
+    """timing = 0 is the production setting: no event records between the kernels, i.e. the launches of consecutive
+    iterations are adjacent in the stream and programmatic dependent launch is in effect across iterations too."""
     dst, src, nrm, _ = _pair(60000, 5)
     icp = cb.Icp(ctx, cb.Cloud(ctx, dst, nrm), cb.Cloud(ctx, src))
     max_d2 = np.float32(0.03**2)
-    for k in (1, 2, 3, 5, 9, 14):
+    for k in (1, 2, 3, 5, 9, 14, 23):
         a = icp.estimate(metric=metric, max_iter=k, tol=0.0, max_d2=max_d2, host_loop=True, **kw)
-        b = icp.estimate(metric=metric, max_iter=k, tol=0.0, max_d2=max_d2, host_loop=False, **kw)
+        b = icp.estimate(metric=metric, max_iter=k, tol=0.0, max_d2=max_d2, host_loop=False, timing=timing, **kw)
         assert a["iterations"] == b["iterations"] == k
         assert a["num_corr"] == b["num_corr"], (k, a["num_corr"], b["num_corr"])
         assert frob(a["T"], b["T"]) < 1e-6, (k, frob(a["T"], b["T"]))
@@ -64,7 +67,7 @@ def test_cached_matches_are_the_exact_nearest_neighbours(cb, ctx, orc, n, max_d,
     max_d2 = np.float32(max_d**2)
     icp.estimate(metric="p2p", max_iter=2, tol=0.0, max_d2=max_d2)
     assert 0 < icp.loop_cache()[2] < n  # the second iteration still searches some queries, but no longer all of them
-    r = icp.estimate(metric="p2p", max_iter=iters, tol=0.0, max_d2=max_d2)
+    r = icp.estimate(metric="p2p", max_iter=iters, tol=0.0, max_d2=max_d2, timing=0)  # production setting (see above)
     T_search, near, searched = icp.loop_cache()
     assert searched < n // 4, searched  # the cache is doing its job by now
     q = orc.transform_points(T_search, src)
