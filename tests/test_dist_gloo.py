@@ -160,3 +160,35 @@ def test_attach_comm_ranks_agree_on_the_exchange_path(tmp_path, failing_rank):
         names = [c[0] for c in calls]
         assert names[:2] == ["init_comm", "ipc_attach"] and calls[1][1] == 64 * world
         assert ("ipc_detach" in names) == (failing_rank >= 0), (rank, names)
+
+
+def _optout_worker(rank, world, port, out_dir, optout_rank):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    os.environ.pop("CB_TEST_IPC_FAIL_RANK", None)
+    os.environ.pop("CB_NO_FUSED_EXCHANGE", None)
+    if rank == optout_rank:
+        os.environ["CB_NO_FUSED_EXCHANGE"] = "1"
+    import torch.distributed as dist
+
+    from cilantro_b200 import capi, dist as cdist
+
+    cdist.init_process_group(backend="gloo")
+    capi.comm_unique_id = lambda: bytes(128)
+    ctx = _FakeCtx(capi, fail_attach=False)
+    cdist.attach_comm(ctx)
+    with open(os.path.join(out_dir, f"optout_{rank}.txt"), "w") as f:
+        f.write(repr(ctx.calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_attach_comm_one_rank_opting_out_keeps_every_rank_on_nccl(tmp_path):
+    """CB_NO_FUSED_EXCHANGE set on ONE rank only: no rank may map the peer tables (a rank on the fused path would wait
+    for a row its peer sends through NCCL instead) - the setting is agreed on before anyone attaches."""
+    world = 2
+    mp.spawn(_optout_worker, args=(world, _free_port(), str(tmp_path), 1), nprocs=world, join=True)
+    for rank in range(world):
+        names = [c[0] for c in eval(open(tmp_path / f"optout_{rank}.txt").read())]
+        assert names == ["init_comm"], (rank, names)
