@@ -34,6 +34,15 @@ def test_library_exports_every_declared_symbol(cb):
     assert b"sm_100a" in lib.cb_version()
 
 
+def test_integration_guide_names_every_entry_point():
+    """INTEGRATION.md is the maintainer's binding guide: every declared entry point appears there, either against the
+    reference method it replaces or in the table of entry points without a reference counterpart."""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        guide = f.read()
+    missing = [s for s in _declared_symbols() if s not in guide]
+    assert not missing, f"not mentioned in INTEGRATION.md: {missing}"
+
+
 def test_no_cpu_fallback_without_device(cb):
     import torch
 
