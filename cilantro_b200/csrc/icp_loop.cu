@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kBlock, CB_WARM_MIN_BLOCKS) icp_cached_kernel(
 
 // ---- the cached pass, asynchronous-copy pipeline (the shipped version) ---------------------------------------------------
 // Same arithmetic, same tile walk, same flags and sums as icp_cached_kernel above; what changes is how the data gets
-// to the thread. ncu on the register version (profiles/r02_icp_cached_kernel.md): 128 registers -> 2 blocks/SM, 24 %
+// to the thread. ncu on the register version (an early round-2 capture): 128 registers -> 2 blocks/SM, 24 %
 // of the warp slots occupied, long-scoreboard the top stall, 27 % of the DRAM bandwidth - each thread can only keep
 // the loads in flight that it has registers for. Here every thread runs a private three-deep pipeline of
 // cp.async copies into shared memory (LDGSTS: no destination register, no scoreboard slot):
