@@ -11,7 +11,12 @@
 // this restatement:
 //   * kNN: the reference's own vendored nanoflann 1.7.1, compiled in place into
 //     oracle/_ref/ (oracle/nanoflann_ref.cpp) — orc_knn1_brute must agree with it on every
-//     query (equal index, or bit-equal d2 on exact ties), see tests/test_oracle_knn.py;
+//     query (equal index, or bit-equal d2 on exact ties), see tests/test_oracle_kat.py
+//     (test_brute_restatement_agrees_with_reference_nanoflann); the full-size runs of BASELINE's configs 2 and 3
+//     (tests/test_gpu_full_size.py) search with that reference nanoflann inside the restated loop;
+//   * the correspondence-weight evaluators (Unity / RBFKernelWeightEvaluator, common_pair_evaluators.hpp:54-60) and
+//     the weighted normal equations: an independent numpy restatement of transform_estimation.hpp:285-357
+//     (tests/test_oracle_rbf.py);
 //   * the hand-derivable known answers of examples/kd_tree.cpp and
 //     examples/principal_component_analysis.cpp (tests/test_oracle_kat.py);
 //   * the self-checking recipe of examples/rigid_icp.cpp (estimate ~= tf_ref^-1);
