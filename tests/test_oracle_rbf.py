@@ -61,12 +61,16 @@ def _gn_step_numpy(dst, nrm, src, w_pt, w_pl, max_d2, pt_sigma, pl_sigma):
     return np.hstack([U @ Vt, t[:, None]]), int(keep.sum())
 
 
-@pytest.mark.parametrize("sig", [(None, None), (0.05, None), (None, 0.03), (0.04, 0.06)])
-@pytest.mark.parametrize("weights", [(0.0, 1.0), (0.3, 1.0), (1.0, 0.0)])
+_SIGMAS = [(None, None), (0.05, None), (None, 0.03), (0.04, 0.06)]
+_WEIGHTS = [(0.0, 1.0), (0.3, 1.0), (1.0, 0.0)]
+# an evaluator on a switched-off term (metric weight 0) is never read: those combinations are not cases
+_CASES = [(w, s) for w in _WEIGHTS for s in _SIGMAS
+          if not ((w[0] == 0.0 and s[0] is not None) or (w[1] == 0.0 and s[1] is not None))]
+
+
+@pytest.mark.parametrize("weights,sig", _CASES)
 def test_weighted_gauss_newton_step_matches_numpy(orc, sig, weights):
     w_pt, w_pl = weights
-    if (w_pt == 0.0 and sig[0] is not None) or (w_pl == 0.0 and sig[1] is not None):
-        pytest.skip("evaluator of a switched-off term")
     rng = np.random.default_rng(17)
     dst = rng.random((400, 3)).astype(np.float32)
     g = rng.standard_normal((400, 3))
