@@ -437,9 +437,10 @@ def icp_bench(args, name, w, scaling, ctx, rank, world, local, with_e2e=True, wi
                 # DRAM bytes of one converged iteration's kernels (cached pass + search + finish), ncu --set full
                 "traffic": (tr.get("converged_iteration") or {}).get("total") if world == 1 else None,
                 "traffic_detail": tr if world == 1 else None,
-                "kernel": ("one ICP iteration = icp_cached_kernel<%s> (exact re-use of the previous matches) + "
-                           "icp_search_kernel<%s> (grid 1-NN of the remaining queries, reduction, exchange, solve); "
-                           "the first iteration of a call is icp_search_kernel alone" % (w["metric"], w["metric"])),
+                "kernel": ("one ICP iteration = icp_cached_pipe_kernel<%s> (exact re-use of the previous matches) + "
+                           "icp_search_kernel<%s> (grid 1-NN of the remaining queries, grid reduction) + "
+                           "icp_finish_kernel (one warp: exchange over NVLink, solve); the first iteration of a call is "
+                           "icp_search_kernel + icp_finish_kernel alone" % (w["metric"], w["metric"])),
                 "kernel_ms": ms_per_step, "algorithmic_bytes": algo_bytes, "peak_source": peak_src,
                 "first_iteration": frac(cold_ms), "converged_iterations": frac(warm_ms),
                 "iter_ms": [float(x) for x in iter_ms]}
