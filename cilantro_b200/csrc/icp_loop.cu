@@ -808,7 +808,9 @@ int icp_loop_estimate(cb_icp* icp, const cb_icp_params* prm, cb_icp_result* res,
   if (cached_regs) {
     blocks_cached = std::max(1, std::min(ctx->sm_count * CB_WARM_MIN_BLOCKS, (int)((ns + kWarmTile - 1) / kWarmTile)));
   } else {
-    static bool attr_set = false;
+    // once per device (function attributes belong to the device the context is on, not to the process)
+    static bool attr_set_dev[64] = {};
+    bool& attr_set = attr_set_dev[ctx->device & 63];
     if (!attr_set) {
       CB_CUDA(cudaFuncSetAttribute(icp_cached_pipe_kernel<kModeP2PCentered>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(PipeSmem<false>)));

@@ -325,14 +325,11 @@ extern "C" int cb_cloud_estimate_normals(cb_context* ctx, cb_cloud* cloud, int k
   else if (k <= 32)
     normals_knn_kernel<32><<<blocks, kBlock, 32 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
   else if (k <= 64) {
-    static const cudaError_t attr = cudaFuncSetAttribute(normals_knn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         64 * kBlock * 8);
-    CB_CUDA(attr);
+    // (per call, not once per process: function attributes belong to the device the context is on)
+    CB_CUDA(cudaFuncSetAttribute(normals_knn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * kBlock * 8));
     normals_knn_kernel<64><<<blocks, kBlock, 64 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
   } else {
-    static const cudaError_t attr = cudaFuncSetAttribute(normals_knn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         128 * kBlock * 8);
-    CB_CUDA(attr);
+    CB_CUDA(cudaFuncSetAttribute(normals_knn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * kBlock * 8));
     normals_knn_kernel<128><<<blocks, kBlock, 128 * kBlock * 8, ctx->stream>>>(g, k, max_d2, o);
   }
   ctx->launches += 1;
