@@ -23,6 +23,7 @@
 // 6-ulp error of the fp32 distance evaluation); an exact tie can never pass the strict test.
 // As ICP converges the per-iteration motion shrinks geometrically and almost every query takes the cached path:
 // the iteration becomes one streaming pass (16 B query + 8 B cache + one 16 B gather per source point).
+#include "cache_rule.hpp"
 #include "icp_accumulate.cuh"
 #include "icp_kernels.cuh"
 #include "icp_object.hpp"
@@ -57,9 +58,6 @@ constexpr int kBlock = kReduceBlock;
 constexpr int kQptDense = CB_LOOP_QPT_DENSE;
 constexpr int kQptWarm = CB_LOOP_QPT;
 constexpr int kDenseIters = 1;
-constexpr float kUp18 = 1.0000038146972656f;    // 1 + 2^-18
-constexpr float kDown18 = 0.9999961853027344f;  // 1 - 2^-18
-constexpr float kDown17 = 0.9999923706054688f;  // 1 - 2^-17
 
 struct LoopArgs {
   GridView dst;
@@ -201,7 +199,7 @@ __device__ __forceinline__ ChunkPair search_chunk_body(const LoopArgs& a, const 
     cp.pos = (wb.idx >= 0 && wb.d2 < a.max_d2) ? wb.pos : -1;
     cp.d2 = wb.d2;
     a.cache_pos[cp.i] = cp.pos;
-    a.cache_r[cp.i] = (wb.D2 > 0.f) ? __fmul_rd(__fsqrt_rd(wb.D2), kDown18) : 0.f;
+    a.cache_r[cp.i] = rule::cache_radius(wb.D2);
   }
   return cp;
 }
@@ -321,41 +319,17 @@ __global__ void __launch_bounds__(kBlock, CB_WARM_MIN_BLOCKS) icp_cached_kernel(
       const bool active = i < a.n_src;
       bool miss = active;
       if (active && rc[k] > 0.f) {
-        float qx, qy, qz, ox, oy, oz;
-        apply_rigid(cx.T, sc[k].x, sc[k].y, sc[k].z, qx, qy, qz);
-        apply_rigid(cx.Tp, sc[k].x, sc[k].y, sc[k].z, ox, oy, oz);
-        const float ex = __fsub_rn(qx, ox), ey = __fsub_rn(qy, oy), ez = __fsub_rn(qz, oz);
-        // upper bound of the distance the query moved since the previous iteration
-        const float dl = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex)))), kUp18);
-        const float r2 = __fsub_rd(rc[k], dl);
-        if (r2 > 0.f) {
-          // every reference point other than `seed` has a computed d2 above lim under the current transform
-          const float lim = __fmul_rd(__fmul_rd(r2, r2), kDown17);
-          bool pair = false;
-          float d2 = 0.f;
-          if (sd[k] >= 0) {
-            const float dx = __fsub_rn(qx, p[k].x), dy = __fsub_rn(qy, p[k].y), dz = __fsub_rn(qz, p[k].z);
-            d2 = __fmul_rn(dx, dx);
-            d2 = __fadd_rn(d2, __fmul_rn(dy, dy));
-            d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
-            if (d2 < a.max_d2) {
-              if (d2 < lim) {  // still the unique nearest neighbour, inside the radius
-                miss = false;
-                pair = true;
-              }
-            } else if (a.max_d2 <= lim) {  // the match left the radius and nothing else is inside it
-              miss = false;
-            }
-          } else if (a.max_d2 <= lim) {  // nothing was within the radius and nothing can have entered it
-            miss = false;
-          }
-          if (!miss) a.cache_r[i] = r2;
-          if (pair) {
-            const float4 nk = pn[k];
-            accumulate_pair<MODE, true>(
-                acc, cx, a.has_pt != 0, a.has_pl != 0, p[k], qx, qy, qz, a.src_nrm != nullptr, [&] { return nk; },
-                [&] { return __ldg(a.src_nrm + i); }, d2);
-          }
+        // the exclusion test (cache_rule.hpp): hit -> the cached match is this iteration's exact search result
+        rule::Verdict v;
+        float4 pm = p[k];
+        rule::cached_match_test(cx.T, cx.Tp, sc[k].x, sc[k].y, sc[k].z, rc[k], sd[k], a.max_d2, [&] { return p[k]; }, pm, v);
+        miss = v.miss;
+        if (!miss) a.cache_r[i] = v.r2;
+        if (v.pair) {
+          const float4 nk = pn[k];
+          accumulate_pair<MODE, true>(
+              acc, cx, a.has_pt != 0, a.has_pl != 0, pm, v.qx, v.qy, v.qz, a.src_nrm != nullptr, [&] { return nk; },
+              [&] { return __ldg(a.src_nrm + i); }, v.d2);
         }
       }
       const unsigned int mm = __ballot_sync(0xffffffffu, miss);
@@ -501,43 +475,17 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeCombined) ? 3 : 4) icp_c
         const int sd = ps.seed[abuf][slot];
         if (rc > 0.f) {
           const float4 sc = ps.src[abuf][slot];
-          float qx, qy, qz, ox, oy, oz;
-          apply_rigid(cx.T, sc.x, sc.y, sc.z, qx, qy, qz);
-          apply_rigid(cx.Tp, sc.x, sc.y, sc.z, ox, oy, oz);
-          const float ex = __fsub_rn(qx, ox), ey = __fsub_rn(qy, oy), ez = __fsub_rn(qz, oz);
-          // upper bound of the distance the query moved since the previous iteration
-          const float dl = __fmul_ru(__fsqrt_ru(__fmaf_ru(ez, ez, __fmaf_ru(ey, ey, __fmul_ru(ex, ex)))), kUp18);
-          const float r2 = __fsub_rd(rc, dl);
-          if (r2 > 0.f) {
-            // every reference point other than `seed` has a computed d2 above lim under the current transform
-            const float lim = __fmul_rd(__fmul_rd(r2, r2), kDown17);
-            bool pair = false;
-            float d2 = 0.f;
-            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (sd >= 0) {
-              p = ps.pt[bbuf][slot];
-              const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-              d2 = __fmul_rn(dx, dx);
-              d2 = __fadd_rn(d2, __fmul_rn(dy, dy));
-              d2 = __fadd_rn(d2, __fmul_rn(dz, dz));
-              if (d2 < a.max_d2) {
-                if (d2 < lim) {  // still the unique nearest neighbour, inside the radius
-                  miss = false;
-                  pair = true;
-                }
-              } else if (a.max_d2 <= lim) {  // the match left the radius and nothing else is inside it
-                miss = false;
-              }
-            } else if (a.max_d2 <= lim) {  // nothing was within the radius and nothing can have entered it
-              miss = false;
-            }
-            if (!miss) a.cache_r[i] = r2;
-            if (pair) {
-              accumulate_pair<MODE, true>(
-                  acc, cx, a.has_pt != 0, a.has_pl != 0, p, qx, qy, qz, a.src_nrm != nullptr,
-                  [&] { return kNormals ? ps.nr[kNormals ? bbuf : 0][kNormals ? slot : 0] : make_float4(0.f, 0.f, 0.f, 0.f); },
-                  [&] { return __ldg(a.src_nrm + i); }, d2);
-            }
+          // the exclusion test (cache_rule.hpp): hit -> the cached match is this iteration's exact search result
+          rule::Verdict v;
+          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+          rule::cached_match_test(cx.T, cx.Tp, sc.x, sc.y, sc.z, rc, sd, a.max_d2, [&] { return ps.pt[bbuf][slot]; }, p, v);
+          miss = v.miss;
+          if (!miss) a.cache_r[i] = v.r2;
+          if (v.pair) {
+            accumulate_pair<MODE, true>(
+                acc, cx, a.has_pt != 0, a.has_pl != 0, p, v.qx, v.qy, v.qz, a.src_nrm != nullptr,
+                [&] { return kNormals ? ps.nr[kNormals ? bbuf : 0][kNormals ? slot : 0] : make_float4(0.f, 0.f, 0.f, 0.f); },
+                [&] { return __ldg(a.src_nrm + i); }, v.d2);
           }
         }
       }
